@@ -1,0 +1,130 @@
+/*
+ * b200quant.h — C ABI of libb200quant.so, the sm_100a implementation of the
+ * per-layer weight-quantization arithmetic of vimarsh244/llm-quantization.
+ *
+ * The reference has no FFI of its own: its hot path is a set of plain Python
+ * functions built from torch ops.  Every entry point below replaces one such
+ * expression; the `ref:` tag names the reference file:line it stands in for.
+ * The Python modules in llm-quantization_b200/ (same names and signatures as
+ * the reference's) bind these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - matrices are row-major [N rows = out_features, K cols = in_features];
+ *   - `dtype` is the storage type of the weights/activations (B200Q_F32 /
+ *     B200Q_F16 / B200Q_BF16).  Arithmetic follows torch's eager semantics for
+ *     that type: every elementwise op is evaluated in fp32 and rounded to the
+ *     storage type, so fp32 inputs give results bit-identical to torch's;
+ *   - outputs are caller-allocated; optional outputs may be NULL;
+ *   - `stream` is a cudaStream_t passed as void*; no call synchronises;
+ *   - return value: 0 on success, negative B200Q_E* otherwise, with a
+ *     thread-local message from b200q_last_error();
+ *   - there is no CPU path: every entry point launches sm_100a kernels.
+ */
+#ifndef B200QUANT_H_
+#define B200QUANT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200Q_F32 0
+#define B200Q_F16 1
+#define B200Q_BF16 2
+
+#define B200Q_OK 0
+#define B200Q_EINVAL (-1)   /* bad argument (shape, alignment, dtype) */
+#define B200Q_ECUDA (-2)    /* CUDA runtime / launch error */
+#define B200Q_EUNSUPPORTED (-3)
+
+/* pre-/post-operation applied per input column by b200q_group_fakequant */
+#define B200Q_COLOP_NONE 0
+#define B200Q_COLOP_MUL_DIV 1 /* w*=m[k] before, /=m[k] after   ref: awq_quantizer.py:70,81 */
+#define B200Q_COLOP_DIV 2     /* w/=m[k] before, nothing after  ref: smooth_quant_quantizer.py:170 */
+
+const char* b200q_last_error(void);
+int b200q_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t b200q_launch_count(void);
+
+/* ---- torch-CPU log2 semantics, exported for the CPU test-suite -------------------
+ * rne(log2f(r)) and floor(log2f(m)) as torch's CPU kernel evaluates them are step
+ * functions of r; the library tabulates the step positions on the host at load
+ * time (double log2 rounded to float).  These return the bit pattern of the smallest
+ * positive float whose result is >= e+1 (round) / >= e (floor).
+ * ref: pot_apot_quantizer.py:66,88,105 */
+uint32_t b200q_log2_round_threshold_bits(int e);  /* e in [-127,127] */
+uint32_t b200q_log2_floor_threshold_bits(int e);  /* e in [-149,127] */
+
+/* ---- column statistics -------------------------------------------------------------
+ * colmax[k] = max_i |W[i,k]|, as fp32.   ref: gptq_quantizer.py:182 (per column over
+ * all rows), smooth_quant_quantizer.py:156.  `accumulate`!=0 keeps the values already
+ * in colmax (running max across row shards / calls); 0 overwrites. */
+int b200q_col_absmax(const void* W, int64_t N, int64_t K, int64_t ld, int dtype,
+                     float* colmax, int accumulate, void* stream);
+
+/* ---- GPTQ column stage, reference-parity semantics ---------------------------------
+ * s[k] = clamp(colmax[k]/(2^b-1), 1e-5); q = clamp(rne(W/s), -2^b, 2^b-1); out = q*s.
+ * ref: gptq_quantizer.py:167-206 (closed form of the column loop; the reference applies
+ * no error compensation, so perm/blocksize/H do not reach the output).
+ * codes (int8, optional) and scales (fp32 [K], optional) expose the integers. */
+int b200q_gptq_parity_quant(const void* W, void* out, int8_t* codes, const float* colmax,
+                            float* scales, int64_t N, int64_t K, int64_t ld, int n_bit,
+                            int dtype, void* stream);
+
+/* ---- uniform group fake-quant ------------------------------------------------------
+ * asymmetric (symmetric=0): ref quantization_utils.py:362-413 (pseudo_quantize_tensor)
+ * symmetric  (symmetric=1): ref gptq_quantizer.py:79-108 (_simple_quantize_layer)
+ * W is [N,K]; groups are `group` consecutive elements of a row (K % group == 0);
+ * group <= 0 means one group per row.  colop/colvec: see B200Q_COLOP_*.
+ * codes: uint8 (asym, [0,2^b-1]) or int8 (sym) when n_bit<=8; scales/zeros fp32 per group. */
+int b200q_group_fakequant(const void* W, void* out, void* codes, float* scales, float* zeros,
+                          int64_t N, int64_t K, int64_t group, int n_bit, int symmetric,
+                          int colop, const float* colvec, int dtype, void* stream);
+
+/* ---- SmoothQuant --------------------------------------------------------------------
+ * s[k] = clamp( clamp(a[k],1e-5)^alpha / clamp(wmax[k],1e-5)^(1-alpha), 1e-5 )
+ * ref: smooth_quant_quantizer.py:159-166.  act_dtype / w_dtype give the precision each
+ * pow is rounded to (torch evaluates them in the tensors' own types). */
+int b200q_smooth_scale(const float* act_scale, const float* wmax, float* s, int64_t K,
+                       float alpha, int act_dtype, int w_dtype, void* stream);
+/* out[i,k] = W[i,k] / s[k]   ref: smooth_quant_quantizer.py:170 ; mul!=0: W*s (:251) */
+int b200q_col_scale(const void* W, void* out, const float* s, int64_t N, int64_t K, int mul,
+                    int dtype, void* stream);
+
+/* ---- activation statistics ---------------------------------------------------------
+ * X is [T,K].  meanabs: ref quantization_utils.py:231 ; maxabs: ref
+ * smooth_quant_quantizer.py:68 (+ running max :74 when accumulate!=0). fp32 out. */
+int64_t b200q_act_stat_workspace(int64_t T, int64_t K); /* bytes of device scratch for meanabs */
+int b200q_act_meanabs(const void* X, int64_t T, int64_t K, int dtype, float* out, void* work,
+                      void* stream);
+int b200q_act_maxabs(const void* X, int64_t T, int64_t K, int dtype, float* out, int accumulate,
+                     void* stream);
+/* out[k] = ((0 + V[0,k]) + V[1,k]) + ... sequential, each partial sum rounded to V's dtype: the
+ * order and precision of Python's sum() over a list of [K] tensors.   ref: awq_quantizer.py:57 */
+int b200q_seq_sum_rows(const void* V, int64_t n, int64_t K, int dtype, float* out, void* stream);
+
+/* ---- POT ------------------------------------------------------------------------------
+ * ref: pot_apot_quantizer.py:25-115.  w is [n_groups, group] contiguous; grid_host is the
+ * HOST array torch.arange(0.01, 2.01, 0.01) materialised by the caller (n_grid floats).
+ * Outputs: out (same dtype), exps (uint8 exponent code E, optional), best_scale (fp32 per
+ * group, optional), best_idx (int32 per group, -1 = no candidate beat +inf, optional). */
+int b200q_pot_quant(const void* w, void* out, uint8_t* exps, float* best_scale, int32_t* best_idx,
+                    int64_t n_groups, int64_t group, int n_bit, const float* grid_host,
+                    int n_grid, int dtype, void* stream);
+
+/* ---- APOT -----------------------------------------------------------------------------
+ * ref: pot_apot_quantizer.py:192-351.  levels_host: the signed, normalised, sorted level
+ * set (<= 32 entries) built by the caller exactly as :227-247; grid_host as :262.
+ * Outputs: out, level index per element (uint8, optional), best_scale, best_idx. */
+int b200q_apot_quant(const void* w, void* out, uint8_t* level_idx, float* best_scale,
+                     int32_t* best_idx, int64_t n_groups, int64_t group,
+                     const float* levels_host, int n_levels, const float* grid_host, int n_grid,
+                     int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200QUANT_H_ */

@@ -1,0 +1,109 @@
+"""awq_quantizer — drop-in for the reference module of the same name.
+
+`awq_quantize_model_weight` keeps the reference's semantics exactly (awq_quantizer.py:22-84):
+importance = Python-sum of the per-batch mean|x| vectors, top-k salient input channels, scale them
+up, asymmetric group fake-quant, scale them back.  On the B200 the three weight passes are ONE
+kernel (b200q_group_fakequant with the MUL_DIV column op) and the importance sum is one kernel that
+reproduces sum()'s left-to-right order.
+
+`awq_search_scale_factor` is a stub in the reference (returns the midpoint).  Here it performs the
+search its docstring describes (awq_quantizer.py:116-119) with the fused quantize + output-MSE
+tensor-core kernel; set SEARCH_STUB = True to get the reference's midpoint back.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+from typing import Dict, List, Tuple
+
+import torch
+import torch.nn as nn
+
+_HERE = Path(__file__).resolve().parent
+if str(_HERE) not in sys.path:
+    sys.path.insert(0, str(_HERE))
+
+from b200q import ops as _ops  # noqa: E402
+from b200q import pipeline as _pipeline  # noqa: E402
+from quantization_utils import pseudo_quantize_tensor  # noqa: E402,F401  (re-exported like the reference)
+
+SEARCH_STUB = False
+
+
+def _importance(feats: List[torch.Tensor], device) -> torch.Tensor:
+    """sum(list of [K] tensors).float(), evaluated left to right in the tensors' own dtype."""
+    if isinstance(feats, torch.Tensor):       # an [n, K] tensor iterates (and sums) row by row
+        stacked = feats.reshape(feats.shape[0], -1)
+    else:
+        stacked = torch.stack([f.reshape(-1) for f in feats])
+    return _ops.seq_sum_rows(stacked.to(device, non_blocking=True))
+
+
+def _salient_channels(importance: torch.Tensor, protect_ratio: float) -> torch.Tensor:
+    n_protect = max(1, int(importance.numel() * protect_ratio))
+    return torch.topk(importance, n_protect)[1]
+
+
+@torch.no_grad()
+def awq_quantize_model_weight(
+    model: nn.Module,
+    w_bit: int,
+    q_group_size: int,
+    input_feat: Dict[str, List[torch.Tensor]],
+    protect_ratio: float = 0.01,
+    scale_factor: float = 1.0,
+) -> None:
+    """AWQ-protect and fake-quantize every calibrated nn.Linear in place; Linears without
+    calibration features are left untouched (reference: awq_quantizer.py:50-54)."""
+    def compute(name, _module, W):
+        if q_group_size > 0:
+            assert W.shape[-1] % q_group_size == 0
+        salient = _salient_channels(_importance(input_feat[name], W.device), protect_ratio)
+        assert salient.dim() == 1
+        colmul = torch.ones(W.shape[1], dtype=torch.float32, device=W.device)
+        colmul[salient] = float(scale_factor)
+        return _ops.group_fakequant(W, w_bit, q_group_size, colop=_ops.COLOP_MUL_DIV, colvec=colmul)
+
+    _pipeline.run_layers([(n, m) for n, m in model.named_modules()
+                          if isinstance(m, nn.Linear) and n in input_feat], compute)
+
+
+@torch.no_grad()
+def awq_search_scale_factor(
+    model: nn.Module,
+    w_bit: int,
+    q_group_size: int,
+    input_feat: Dict[str, List[torch.Tensor]],
+    protect_ratio: float = 0.01,
+    scale_search_range: Tuple[float, float] = (1.0, 2.0),
+    n_grid: int = 20,
+) -> float:
+    """Grid-search the AWQ scale factor: for each of `n_grid` candidates in `scale_search_range`
+    quantize every calibrated Linear and add up the output reconstruction error
+    ||(Q(W) - W) X^T||^2 against the calibration features; return the candidate with the smallest
+    total.  The model is not modified."""
+    print("Searching for optimal scale factor...")
+    lo, hi = scale_search_range
+    if SEARCH_STUB:
+        best = (lo + hi) / 2.0
+        print(f"  -> Using scale factor: {best:.3f}")
+        return best
+    from b200q import tensor_ops as _tops
+    candidates = torch.linspace(float(lo), float(hi), int(n_grid), dtype=torch.float64).tolist()
+    total = None
+    for name, module in model.named_modules():
+        if not isinstance(module, nn.Linear) or name not in input_feat:
+            continue
+        W = _ops.to_device(module.weight.data)
+        feats = input_feat[name]
+        salient = _salient_channels(_importance([f.abs().reshape(-1, f.shape[-1]).mean(0)
+                                                 if f.dim() > 1 else f for f in feats], W.device),
+                                    protect_ratio)
+        loss = _tops.awq_search_losses(W, feats, salient, w_bit, q_group_size, candidates)
+        total = loss if total is None else total + loss
+    if total is None:
+        best = (lo + hi) / 2.0
+    else:
+        best = candidates[int(torch.argmin(total).item())]
+    print(f"  -> Using scale factor: {best:.3f}")
+    return float(best)

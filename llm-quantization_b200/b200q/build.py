@@ -1,0 +1,86 @@
+"""Build libb200quant.so in-tree with nvcc for sm_100a.
+
+The library is plain CUDA C++ with a C ABI (include/b200quant.h); it links only libcudart, so it
+cross-compiles on a machine without a GPU and travels to the B200 box as a prebuilt file.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent.parent          # llm-quantization_b200/
+CSRC = PKG_DIR / "csrc"
+REPO = PKG_DIR.parent
+LIB_PATH = PKG_DIR / "libb200quant.so"
+OBJ_DIR = CSRC / "build"
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
+          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+# per-file extra flags.  The elementwise / level-search kernels must round every op separately to
+# stay bit-identical with torch (no FMA contraction); the GEMM-shaped kernels want FMAs.
+SOURCES = {
+    "core.cu": [],
+    "elementwise.cu": ["-fmad=false"],
+    "levels.cu": ["-fmad=false"],
+    "tensorcore.cu": [],
+    "linalg.cu": [],
+}
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libb200quant.so cannot be built (no CPU fallback exists)")
+
+
+def _stale(target: Path, deps) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(d).stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every .cu under csrc/ for sm_100a and link libb200quant.so. Returns its path."""
+    nvcc = _nvcc()
+    OBJ_DIR.mkdir(exist_ok=True)
+    headers = list(CSRC.glob("*.cuh")) + [REPO / "include" / "b200quant.h"]
+    objs = []
+    log_lines = []
+    for name, extra in SOURCES.items():
+        src = CSRC / name
+        if not src.exists():
+            continue
+        obj = OBJ_DIR / (src.stem + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [src, *headers]):
+            cmd = [nvcc, *ARCH, *COMMON, *extra, "-I", str(REPO / "include"), "-c", str(src),
+                   "-o", str(obj)]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            log_lines.append("$ " + " ".join(cmd))
+            log_lines.append(res.stderr)
+            if res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+                raise RuntimeError(f"nvcc failed on {name}")
+            if verbose:
+                print(res.stderr)
+    if force or _stale(LIB_PATH, objs):
+        cmd = [nvcc, *ARCH, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-lcudart", "-lcuda"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("link of libb200quant.so failed")
+    if log_lines:
+        (OBJ_DIR / "ptxas.log").write_text("\n".join(log_lines))
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(p)

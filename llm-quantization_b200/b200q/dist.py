@@ -1,0 +1,89 @@
+"""Row-sharded execution over several GPUs (one process per GPU, torch.distributed / NCCL).
+
+The quantizers shard a Linear's OUTPUT rows: each rank holds W[r0:r1, :].  Rows are independent in
+every method except for three small exchanges, which are the only collectives on the path:
+
+  * GPTQ (parity) and SmoothQuant use a per-input-column |max| over ALL rows
+    (gptq_quantizer.py:182, smooth_quant_quantizer.py:156)           -> all-reduce MAX of fp32 [K]
+  * the GPTQ Hessian is accumulated over calibration samples, which are dealt round-robin to the
+    ranks                                                            -> all-reduce SUM of fp32 [K,K]
+    and its inverse is computed once and shared                      -> broadcast of fp32 [K,K]
+  * the AWQ scale search adds per-candidate losses over row shards   -> all-reduce SUM of [n_cand]
+  * APOT picks its grid from the element count of the WHOLE tensor (pot_apot_quantizer.py:258)
+                                                                     -> all-reduce SUM of one int
+
+Outside a `row_sharded()` block every helper is the identity, so the single-GPU path pays nothing.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Optional
+
+import torch
+import torch.distributed as td
+
+_active_group = None
+_active = False
+
+
+@contextlib.contextmanager
+def row_sharded(group: Optional["td.ProcessGroup"] = None):
+    """Mark the enclosed quantizer calls as operating on this rank's row shard of every weight."""
+    global _active, _active_group
+    if not (td.is_available() and td.is_initialized()):
+        raise RuntimeError("row_sharded() needs an initialised torch.distributed process group")
+    prev = (_active, _active_group)
+    _active, _active_group = True, group
+    try:
+        yield
+    finally:
+        _active, _active_group = prev
+
+
+def is_sharded() -> bool:
+    return _active and td.get_world_size(_active_group) > 1
+
+
+def world_size() -> int:
+    return td.get_world_size(_active_group) if _active else 1
+
+
+def rank() -> int:
+    return td.get_rank(_active_group) if _active else 0
+
+
+def allreduce_max(t: torch.Tensor) -> torch.Tensor:
+    if is_sharded():
+        td.all_reduce(t, op=td.ReduceOp.MAX, group=_active_group)
+    return t
+
+
+def allreduce_sum(t: torch.Tensor) -> torch.Tensor:
+    if is_sharded():
+        td.all_reduce(t, op=td.ReduceOp.SUM, group=_active_group)
+    return t
+
+
+def broadcast(t: torch.Tensor, src: int = 0) -> torch.Tensor:
+    if is_sharded():
+        td.broadcast(t, src=td.get_global_rank(_active_group, src) if _active_group else src,
+                     group=_active_group)
+    return t
+
+
+def global_numel(local_numel: int, device) -> int:
+    """Element count of the whole (unsharded) tensor."""
+    if not is_sharded():
+        return local_numel
+    n = torch.tensor([local_numel], dtype=torch.int64, device=device)
+    td.all_reduce(n, op=td.ReduceOp.SUM, group=_active_group)
+    return int(n.item())
+
+
+def shard_rows(n_rows: int, world: Optional[int] = None, r: Optional[int] = None):
+    """Contiguous, near-equal row range [r0, r1) of rank r."""
+    world = world_size() if world is None else world
+    r = rank() if r is None else r
+    base, extra = divmod(n_rows, world)
+    r0 = r * base + min(r, extra)
+    return r0, r0 + base + (1 if r < extra else 0)

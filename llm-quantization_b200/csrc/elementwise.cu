@@ -1,0 +1,722 @@
+// HBM-bound stages: column |max|, GPTQ parity column quantisation, uniform group fake-quant
+// (pseudo_quantize_tensor / _simple_quantize_layer, with AWQ and SmoothQuant column ops fused),
+// SmoothQuant scale + migration, activation statistics.
+//
+// Design: every kernel moves 128 bits per thread per access (ld.global.nc.L1::no_allocate /
+// st.global.L1::no_allocate), keeps >=4 independent loads in flight per thread, and is launched
+// with a grid that is a multiple of the 148 SMs where the shape allows.  Arithmetic follows torch's
+// eager op sequence exactly (IEEE div, rint = half-to-even, no FMA contraction: this file is
+// compiled with -fmad=false), so fp32 results are bit-identical to the reference's.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace b200q {
+
+// =================================================================================================
+// column abs-max  (ref: gptq_quantizer.py:182, smooth_quant_quantizer.py:156,68)
+// =================================================================================================
+// block = 32 column-lanes x 8 row-lanes; a warp reads 512 contiguous bytes of one row.
+template <typename T, bool ABS_ONLY>
+__global__ void __launch_bounds__(256)
+col_absmax_kernel(const T* __restrict__ W, int64_t N, int64_t K, int64_t ld, int rows_per_block,
+                  unsigned int* __restrict__ colmax_bits) {
+  constexpr int VEC = ST<T>::VEC;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t col0 = ((int64_t)blockIdx.x * 32 + tx) * VEC;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(N, r0 + (int64_t)rows_per_block);
+  float m[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) m[j] = 0.f;
+  if (col0 < K) {
+    const T* p = W + col0;
+    int64_t r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {
+      float a[4][VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load_vec<T>(p + (r + 8 * u) * ld, a[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) m[j] = fmaxf(m[j], fabsf(a[u][j]));
+    }
+    for (; r < r1; r += 8) {
+      float a[VEC];
+      load_vec<T>(p + r * ld, a);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) m[j] = fmaxf(m[j], fabsf(a[j]));
+    }
+  }
+  __shared__ float sm[8][32 * VEC + 1];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) sm[ty][tx * VEC + j] = m[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * VEC; c += 256) {
+    const int64_t col = (int64_t)blockIdx.x * 32 * VEC + c;
+    if (col < K) {
+      float v = sm[0][c];
+#pragma unroll
+      for (int y = 1; y < 8; ++y) v = fmaxf(v, sm[y][c]);
+      // non-negative floats order like their bit patterns
+      atomicMax(colmax_bits + col, __float_as_uint(v));
+    }
+  }
+}
+
+// any alignment / leading dimension: one thread per column, rows chunked over blockIdx.y
+template <typename T>
+__global__ void __launch_bounds__(256)
+col_absmax_scalar_kernel(const T* __restrict__ W, int64_t N, int64_t K, int64_t ld,
+                         int rows_per_block, unsigned int* __restrict__ colmax_bits) {
+  const int64_t col = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (col >= K) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(N, r0 + (int64_t)rows_per_block);
+  float m = 0.f;
+  for (int64_t r = r0; r < r1; ++r) m = fmaxf(m, fabsf(to_f(W[r * ld + col])));
+  atomicMax(colmax_bits + col, __float_as_uint(m));
+}
+
+static int pick_rows_per_block(int64_t N, int64_t col_tiles) {
+  // aim for ~8 CTAs per SM worth of blocks, at least 32 rows each
+  const int64_t want_blocks = (int64_t)kNumSMs * 8;
+  int64_t chunks = std::max<int64_t>(1, want_blocks / std::max<int64_t>(1, col_tiles));
+  int64_t rpb = (N + chunks - 1) / chunks;
+  rpb = std::max<int64_t>(32, (rpb + 31) / 32 * 32);
+  return (int)std::min<int64_t>(rpb, 1 << 20);
+}
+
+template <typename T>
+static int launch_col_absmax(const void* Wv, int64_t N, int64_t K, int64_t ld, float* colmax,
+                             int accumulate, cudaStream_t st) {
+  constexpr int VEC = ST<T>::VEC;
+  const T* W = static_cast<const T*>(Wv);
+  if (!accumulate) cudaMemsetAsync(colmax, 0, sizeof(float) * K, st);
+  const bool vec_ok = aligned16(W) && (K % VEC == 0) && (ld % VEC == 0);
+  if (vec_ok) {
+    const int64_t col_tiles = (K + 32 * VEC - 1) / (32 * VEC);
+    const int rpb = pick_rows_per_block(N, col_tiles);
+    dim3 grid((unsigned)col_tiles, (unsigned)((N + rpb - 1) / rpb));
+    col_absmax_kernel<T, true><<<grid, 256, 0, st>>>(W, N, K, ld, rpb,
+                                                     reinterpret_cast<unsigned int*>(colmax));
+  } else {
+    const int64_t col_tiles = (K + 255) / 256;
+    const int rpb = pick_rows_per_block(N, col_tiles);
+    dim3 grid((unsigned)col_tiles, (unsigned)((N + rpb - 1) / rpb));
+    col_absmax_scalar_kernel<T><<<grid, 256, 0, st>>>(W, N, K, ld, rpb,
+                                                      reinterpret_cast<unsigned int*>(colmax));
+  }
+  count_launch();
+  return check_launch("col_absmax");
+}
+
+// =================================================================================================
+// GPTQ column stage, reference-parity semantics (ref: gptq_quantizer.py:167-206)
+// =================================================================================================
+template <typename T>
+__device__ __forceinline__ float clamp_min_1e5() {
+  return ST<T>::rnd(1e-5f);  // torch casts the python scalar to the tensor's dtype
+}
+
+template <typename T, bool VECTOR>
+__global__ void __launch_bounds__(256)
+gptq_parity_kernel(const T* __restrict__ W, T* __restrict__ out, int8_t* __restrict__ codes,
+                   const float* __restrict__ colmax, float* __restrict__ scales, int64_t N,
+                   int64_t K, int64_t ld, float maxint, int rows_per_block) {
+  constexpr int VEC = VECTOR ? ST<T>::VEC : 1;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t col0 = ((int64_t)blockIdx.x * 32 + tx) * VEC;
+  if (col0 >= K) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(N, r0 + (int64_t)rows_per_block);
+  float s[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    // scale = clamp(max_val / max_int, min=1e-5)      gptq_quantizer.py:182-184
+    s[j] = fmaxf(ST<T>::rnd(__fdiv_rn(colmax[col0 + j], maxint)), clamp_min_1e5<T>());
+  }
+  if (scales != nullptr && blockIdx.y == 0 && ty == 0) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) scales[col0 + j] = s[j];
+  }
+  const float lo = -maxint - 1.f, hi = maxint;
+  if constexpr (VECTOR) {
+    int64_t r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {
+      float a[4][ST<T>::VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load_vec<T>(W + (r + 8 * u) * ld + col0, a[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float q[ST<T>::VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          // clamp(round(w / scale), -max_int-1, max_int) * scale    gptq_quantizer.py:187-188
+          q[j] = clampf(rintf(ST<T>::rnd(__fdiv_rn(a[u][j], s[j]))), lo, hi);
+          a[u][j] = ST<T>::rnd(q[j] * s[j]);
+        }
+        store_vec<T>(out + (r + 8 * u) * K + col0, a[u]);
+        if (codes != nullptr) {
+          int8_t* c = codes + (r + 8 * u) * K + col0;
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) c[j] = (int8_t)q[j];
+        }
+      }
+    }
+    for (; r < r1; r += 8) {
+      float a[ST<T>::VEC], q[ST<T>::VEC];
+      load_vec<T>(W + r * ld + col0, a);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        q[j] = clampf(rintf(ST<T>::rnd(__fdiv_rn(a[j], s[j]))), lo, hi);
+        a[j] = ST<T>::rnd(q[j] * s[j]);
+      }
+      store_vec<T>(out + r * K + col0, a);
+      if (codes != nullptr) {
+        int8_t* c = codes + r * K + col0;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) c[j] = (int8_t)q[j];
+      }
+    }
+  } else {
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const float w = to_f(W[r * ld + col0]);
+      const float q = clampf(rintf(ST<T>::rnd(__fdiv_rn(w, s[0]))), lo, hi);
+      out[r * K + col0] = from_f<T>(q * s[0]);
+      if (codes != nullptr) codes[r * K + col0] = (int8_t)q;
+    }
+  }
+}
+
+// =================================================================================================
+// uniform group fake-quant
+//   asym: ref quantization_utils.py:390-405       sym: ref gptq_quantizer.py:94-100
+// =================================================================================================
+struct GroupQuantArgs {
+  float maxint;
+  int64_t n_groups;
+  int64_t G;   // elements per group
+  int64_t K;   // row length (for column ops)
+  const float* colvec;
+  void* codes;
+  float* scales;
+  float* zeros;
+};
+
+template <typename T, int COLOP>
+__device__ __forceinline__ float pre_op(float w, float cv) {
+  if constexpr (COLOP == B200Q_COLOP_MUL_DIV) return ST<T>::rnd(w * cv);  // awq_quantizer.py:70
+  if constexpr (COLOP == B200Q_COLOP_DIV) return ST<T>::rnd(__fdiv_rn(w, cv));  // smooth:170
+  return w;
+}
+template <typename T, int COLOP>
+__device__ __forceinline__ float post_op(float o, float cv) {
+  if constexpr (COLOP == B200Q_COLOP_MUL_DIV) return ST<T>::rnd(__fdiv_rn(o, cv));  // awq:81
+  return o;
+}
+
+// per-group parameters from the group's min/max (asym) or |max| (sym)
+template <typename T, bool SYM>
+__device__ __forceinline__ void group_params(float mx, float mn, float maxint, float& scale,
+                                             float& zp) {
+  if constexpr (SYM) {
+    // scales = clamp(max_val / max_int, min=1e-5)                 gptq_quantizer.py:94-97
+    scale = fmaxf(ST<T>::rnd(__fdiv_rn(mx, maxint)), clamp_min_1e5<T>());
+    zp = 0.f;
+  } else {
+    // scales = (max - min).clamp(min=1e-5) / max_int               quantization_utils.py:395
+    scale = ST<T>::rnd(__fdiv_rn(fmaxf(ST<T>::rnd(mx - mn), clamp_min_1e5<T>()), maxint));
+    // zeros = (-round(min / scales)).clamp_(0, max_int)            quantization_utils.py:396
+    zp = clampf(-rintf(ST<T>::rnd(__fdiv_rn(mn, scale))), 0.f, maxint);
+  }
+}
+template <typename T, bool SYM>
+__device__ __forceinline__ float quant_one(float x, float scale, float zp, float maxint,
+                                           float& code) {
+  if constexpr (SYM) {
+    code = clampf(rintf(ST<T>::rnd(__fdiv_rn(x, scale))), -maxint - 1.f, maxint);
+    return ST<T>::rnd(code * scale);
+  } else {
+    // w_q = clamp(round(w / scales) + zeros, 0, max_int); w = (w_q - zeros) * scales   :402-405
+    code = clampf(ST<T>::rnd(rintf(ST<T>::rnd(__fdiv_rn(x, scale))) + zp), 0.f, maxint);
+    return ST<T>::rnd(ST<T>::rnd(code - zp) * scale);
+  }
+}
+
+// G == 128: a group is one 128-bit access per lane across 32 (fp32) or 16 (16-bit) lanes.
+template <typename T, bool SYM, int COLOP>
+__global__ void __launch_bounds__(256)
+group128_kernel(const T* __restrict__ W, T* __restrict__ out, GroupQuantArgs a) {
+  constexpr int VEC = ST<T>::VEC;
+  constexpr int LPG = 128 / VEC;   // lanes per group
+  constexpr int GPW = 32 / LPG;    // groups per warp per slot
+  constexpr int ILP = 4;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPG, lig = lane % LPG;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t groups_per_row = a.K / 128;
+  for (int64_t base = warp * (GPW * ILP); base < a.n_groups; base += nwarps * (GPW * ILP)) {
+    float v[ILP][VEC];
+    float cv[ILP][VEC];
+    int64_t g[ILP];
+#pragma unroll
+    for (int u = 0; u < ILP; ++u) {
+      g[u] = base + u * GPW + sub;
+      if (g[u] < a.n_groups) {
+        load_vec<T>(W + g[u] * 128 + lig * VEC, v[u]);
+        if constexpr (COLOP != B200Q_COLOP_NONE) {
+          const float* c = a.colvec + (g[u] % groups_per_row) * 128 + lig * VEC;
+#pragma unroll
+          for (int j = 0; j < VEC; j += 4) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(c + j));
+            cv[u][j] = f.x; cv[u][j + 1] = f.y; cv[u][j + 2] = f.z; cv[u][j + 3] = f.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { v[u][j] = 0.f; cv[u][j] = 1.f; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < ILP; ++u) {
+      float mx, mn;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v[u][j] = pre_op<T, COLOP>(v[u][j], cv[u][j]);
+      if constexpr (SYM) {
+        mx = fabsf(v[u][0]);
+#pragma unroll
+        for (int j = 1; j < VEC; ++j) mx = fmaxf(mx, fabsf(v[u][j]));
+        mn = 0.f;
+      } else {
+        mx = v[u][0]; mn = v[u][0];
+#pragma unroll
+        for (int j = 1; j < VEC; ++j) { mx = fmaxf(mx, v[u][j]); mn = fminf(mn, v[u][j]); }
+      }
+#pragma unroll
+      for (int o = LPG / 2; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if constexpr (!SYM) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      }
+      float scale, zp;
+      group_params<T, SYM>(mx, mn, a.maxint, scale, zp);
+      float code[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float o = quant_one<T, SYM>(v[u][j], scale, zp, a.maxint, code[j]);
+        v[u][j] = post_op<T, COLOP>(o, cv[u][j]);
+      }
+      if (g[u] < a.n_groups) {
+        store_vec<T>(out + g[u] * 128 + lig * VEC, v[u]);
+        if (a.codes != nullptr) {
+          if constexpr (SYM) {
+            int8_t* c = static_cast<int8_t*>(a.codes) + g[u] * 128 + lig * VEC;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) c[j] = (int8_t)code[j];
+          } else {
+            uint8_t* c = static_cast<uint8_t*>(a.codes) + g[u] * 128 + lig * VEC;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) c[j] = (uint8_t)code[j];
+          }
+        }
+        if (lig == 0) {
+          if (a.scales != nullptr) a.scales[g[u]] = scale;
+          if (a.zeros != nullptr) a.zeros[g[u]] = zp;
+        }
+      }
+    }
+  }
+}
+
+// any group length: one warp per group, two passes (the second re-reads through L2).
+template <typename T, bool SYM, int COLOP>
+__global__ void __launch_bounds__(256)
+group_generic_kernel(const T* __restrict__ W, T* __restrict__ out, GroupQuantArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t g = warp; g < a.n_groups; g += nwarps) {
+    const int64_t off = g * a.G;
+    float mx = SYM ? 0.f : -INFINITY, mn = INFINITY;
+    for (int64_t i = lane; i < a.G; i += 32) {
+      float cv = 1.f;
+      if constexpr (COLOP != B200Q_COLOP_NONE) cv = a.colvec[(off + i) % a.K];
+      const float x = pre_op<T, COLOP>(to_f(W[off + i]), cv);
+      if constexpr (SYM) mx = fmaxf(mx, fabsf(x));
+      else { mx = fmaxf(mx, x); mn = fminf(mn, x); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    float scale, zp;
+    group_params<T, SYM>(mx, mn, a.maxint, scale, zp);
+    for (int64_t i = lane; i < a.G; i += 32) {
+      float cv = 1.f;
+      if constexpr (COLOP != B200Q_COLOP_NONE) cv = a.colvec[(off + i) % a.K];
+      const float x = pre_op<T, COLOP>(to_f(W[off + i]), cv);
+      float code;
+      const float o = post_op<T, COLOP>(quant_one<T, SYM>(x, scale, zp, a.maxint, code), cv);
+      out[off + i] = from_f<T>(o);
+      if (a.codes != nullptr) {
+        if constexpr (SYM) static_cast<int8_t*>(a.codes)[off + i] = (int8_t)code;
+        else static_cast<uint8_t*>(a.codes)[off + i] = (uint8_t)code;
+      }
+    }
+    if (lane == 0) {
+      if (a.scales != nullptr) a.scales[g] = scale;
+      if (a.zeros != nullptr) a.zeros[g] = zp;
+    }
+  }
+}
+
+template <typename T, bool SYM, int COLOP>
+static int launch_group_quant(const void* W, void* out, const GroupQuantArgs& a, bool fast128,
+                              cudaStream_t st) {
+  if (a.n_groups == 0) return B200Q_OK;
+  if (fast128) {
+    constexpr int GPW = 32 / (128 / ST<T>::VEC);
+    const int64_t warps_needed = (a.n_groups + GPW * 4 - 1) / (GPW * 4);
+    int64_t blocks = (warps_needed + 7) / 8;
+    blocks = std::min<int64_t>(blocks, (int64_t)kNumSMs * 8 * 4);  // grid-stride beyond 4 waves
+    if (blocks > kNumSMs) blocks = blocks / kNumSMs * kNumSMs;      // whole waves
+    group128_kernel<T, SYM, COLOP><<<(unsigned)blocks, 256, 0, st>>>(
+        static_cast<const T*>(W), static_cast<T*>(out), a);
+  } else {
+    int64_t blocks = (a.n_groups + 7) / 8;
+    blocks = std::min<int64_t>(blocks, (int64_t)kNumSMs * 8 * 4);
+    group_generic_kernel<T, SYM, COLOP><<<(unsigned)blocks, 256, 0, st>>>(
+        static_cast<const T*>(W), static_cast<T*>(out), a);
+  }
+  count_launch();
+  return check_launch("group_fakequant");
+}
+
+// =================================================================================================
+// SmoothQuant
+// =================================================================================================
+// torch.pow(tensor, python_float) has exact special cases (sqrt, x*x, ...): replicate them so the
+// default alpha = 0.5 is bit-exact; a general exponent goes through powf (<= 2 ulp from SLEEF's).
+__device__ __forceinline__ float torch_pow_scalar(float x, float e) {
+  if (e == 0.f) return 1.f;
+  if (e == 1.f) return x;
+  if (e == 0.5f) return __fsqrt_rn(x);
+  if (e == 2.f) return x * x;
+  if (e == 3.f) return x * x * x;
+  if (e == -0.5f) return __fdiv_rn(1.f, __fsqrt_rn(x));
+  if (e == -1.f) return __fdiv_rn(1.f, x);
+  if (e == -2.f) return __fdiv_rn(1.f, x * x);
+  return powf(x, e);
+}
+
+__global__ void smooth_scale_kernel(const float* __restrict__ act, const float* __restrict__ wmax,
+                                    float* __restrict__ s, int64_t K, float alpha, float one_m_alpha,
+                                    int act_dtype, int w_dtype, int res_dtype) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  // act_scale = clamp(act_scale, 1e-5); weight_scale = clamp(weight_scale, 1e-5)   smooth:159-160
+  const float a = fmaxf(act[k], rnd_rt(1e-5f, act_dtype));
+  const float w = fmaxf(wmax[k], rnd_rt(1e-5f, w_dtype));
+  // s = pow(a, alpha) / pow(w, 1 - alpha); s = clamp(s, 1e-5)                       smooth:165-166
+  const float pa = rnd_rt(torch_pow_scalar(a, alpha), act_dtype);
+  const float pw = rnd_rt(torch_pow_scalar(w, one_m_alpha), w_dtype);
+  s[k] = fmaxf(rnd_rt(__fdiv_rn(pa, pw), res_dtype), rnd_rt(1e-5f, res_dtype));
+}
+
+template <typename T, bool MUL, bool VECTOR>
+__global__ void __launch_bounds__(256)
+col_scale_kernel(const T* __restrict__ W, T* __restrict__ out, const float* __restrict__ s,
+                 int64_t N, int64_t K, int rows_per_block) {
+  constexpr int VEC = VECTOR ? ST<T>::VEC : 1;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t col0 = ((int64_t)blockIdx.x * 32 + tx) * VEC;
+  if (col0 >= K) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(N, r0 + (int64_t)rows_per_block);
+  float sv[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) sv[j] = s[col0 + j];
+  if constexpr (VECTOR) {
+    int64_t r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {
+      float a[4][ST<T>::VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load_vec<T>(W + (r + 8 * u) * K + col0, a[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          a[u][j] = ST<T>::rnd(MUL ? a[u][j] * sv[j] : __fdiv_rn(a[u][j], sv[j]));
+        store_vec<T>(out + (r + 8 * u) * K + col0, a[u]);
+      }
+    }
+    for (; r < r1; r += 8) {
+      float a[ST<T>::VEC];
+      load_vec<T>(W + r * K + col0, a);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) a[j] = ST<T>::rnd(MUL ? a[j] * sv[j] : __fdiv_rn(a[j], sv[j]));
+      store_vec<T>(out + r * K + col0, a);
+    }
+  } else {
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const float w = to_f(W[r * K + col0]);
+      out[r * K + col0] = from_f<T>(MUL ? w * sv[0] : __fdiv_rn(w, sv[0]));
+    }
+  }
+}
+
+// =================================================================================================
+// activation statistics (ref: quantization_utils.py:231, smooth_quant_quantizer.py:68)
+// =================================================================================================
+// mean|x| over tokens: stage 1 writes one fp32 partial per (row chunk, column) in a fixed order,
+// stage 2 adds the chunks in order and divides by T -> deterministic, no float atomics.
+template <typename T>
+__global__ void __launch_bounds__(256)
+act_abssum_partial_kernel(const T* __restrict__ X, int64_t Trows, int64_t K, int rows_per_block,
+                          float* __restrict__ partial) {
+  constexpr int VEC = ST<T>::VEC;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t col0 = ((int64_t)blockIdx.x * 32 + tx) * VEC;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(Trows, r0 + (int64_t)rows_per_block);
+  float acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  if (col0 < K) {
+    const T* p = X + col0;
+    int64_t r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {
+      float a[4][VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load_vec<T>(p + (r + 8 * u) * K, a[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] += fabsf(a[u][j]);
+    }
+    for (; r < r1; r += 8) {
+      float a[VEC];
+      load_vec<T>(p + r * K, a);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[j] += fabsf(a[j]);
+    }
+  }
+  __shared__ float sm[8][32 * VEC + 1];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) sm[ty][tx * VEC + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * VEC; c += 256) {
+    const int64_t col = (int64_t)blockIdx.x * 32 * VEC + c;
+    if (col < K) {
+      float v = sm[0][c];
+#pragma unroll
+      for (int y = 1; y < 8; ++y) v += sm[y][c];
+      partial[(int64_t)blockIdx.y * K + col] = v;
+    }
+  }
+}
+
+template <typename T>
+__global__ void act_mean_finish_kernel(const float* __restrict__ partial, int chunks, int64_t K,
+                                       float count, float* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float v = 0.f;
+  for (int c = 0; c < chunks; ++c) v += partial[(int64_t)c * K + k];
+  // torch: sum (rounded to the tensor dtype) then div_ by the row count
+  out[k] = ST<T>::rnd(__fdiv_rn(ST<T>::rnd(v), count));
+}
+
+template <typename T>
+__global__ void seq_sum_rows_kernel(const T* __restrict__ V, int64_t n, int64_t K,
+                                    float* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float v = 0.f;  // Python's sum() starts from int 0; every partial sum is a tensor of V's dtype
+  for (int64_t i = 0; i < n; ++i) v = ST<T>::rnd(v + to_f(V[i * K + k]));
+  out[k] = v;
+}
+
+}  // namespace b200q
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace b200q;
+
+extern "C" {
+
+int b200q_col_absmax(const void* W, int64_t N, int64_t K, int64_t ld, int dtype, float* colmax,
+                     int accumulate, void* stream) {
+  B200Q_REQUIRE(W != nullptr && colmax != nullptr, "col_absmax: null pointer");
+  B200Q_REQUIRE(N >= 0 && K > 0 && ld >= K, "col_absmax: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N == 0) {
+    if (!accumulate) cudaMemsetAsync(colmax, 0, sizeof(float) * K, st);
+    return B200Q_OK;
+  }
+  B200Q_DISPATCH_DTYPE(dtype, T, return launch_col_absmax<T>(W, N, K, ld, colmax, accumulate, st));
+  return B200Q_OK;
+}
+
+int b200q_gptq_parity_quant(const void* W, void* out, int8_t* codes, const float* colmax,
+                            float* scales, int64_t N, int64_t K, int64_t ld, int n_bit, int dtype,
+                            void* stream) {
+  B200Q_REQUIRE(W && out && colmax, "gptq_parity_quant: null pointer");
+  B200Q_REQUIRE(N >= 0 && K > 0 && ld >= K, "gptq_parity_quant: bad shape");
+  B200Q_REQUIRE(n_bit >= 1 && n_bit <= 16, "gptq_parity_quant: n_bit must be in [1,16]");
+  B200Q_REQUIRE(codes == nullptr || n_bit <= 7, "gptq_parity_quant: int8 codes need n_bit <= 7");
+  if (N == 0) return B200Q_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float maxint = (float)((1 << n_bit) - 1);
+  B200Q_DISPATCH_DTYPE(dtype, T, {
+    constexpr int VEC = ST<T>::VEC;
+    const bool vec_ok = aligned16(W) && aligned16(out) && (K % VEC == 0) && (ld % VEC == 0);
+    const int64_t cols_per_block = vec_ok ? 32 * VEC : 32;
+    const int64_t col_tiles = (K + cols_per_block - 1) / cols_per_block;
+    const int rpb = pick_rows_per_block(N, col_tiles);
+    dim3 grid((unsigned)col_tiles, (unsigned)((N + rpb - 1) / rpb));
+    if (vec_ok)
+      gptq_parity_kernel<T, true><<<grid, 256, 0, st>>>(static_cast<const T*>(W),
+                                                        static_cast<T*>(out), codes, colmax, scales,
+                                                        N, K, ld, maxint, rpb);
+    else
+      gptq_parity_kernel<T, false><<<grid, 256, 0, st>>>(static_cast<const T*>(W),
+                                                         static_cast<T*>(out), codes, colmax,
+                                                         scales, N, K, ld, maxint, rpb);
+  });
+  count_launch();
+  return check_launch("gptq_parity_quant");
+}
+
+int b200q_group_fakequant(const void* W, void* out, void* codes, float* scales, float* zeros,
+                          int64_t N, int64_t K, int64_t group, int n_bit, int symmetric, int colop,
+                          const float* colvec, int dtype, void* stream) {
+  B200Q_REQUIRE(W && out, "group_fakequant: null pointer");
+  B200Q_REQUIRE(N >= 0 && K > 0, "group_fakequant: bad shape");
+  B200Q_REQUIRE(n_bit >= 1 && n_bit <= 16, "group_fakequant: n_bit must be in [1,16]");
+  const int64_t G = group > 0 ? group : K;
+  // ref: assert org_w_shape[-1] % q_group_size == 0   (quantization_utils.py:384)
+  B200Q_REQUIRE(K % G == 0, "group_fakequant: in_features not divisible by group size");
+  B200Q_REQUIRE(colop == B200Q_COLOP_NONE || colvec != nullptr, "group_fakequant: colvec missing");
+  B200Q_REQUIRE(colop >= 0 && colop <= 2, "group_fakequant: bad colop");
+  B200Q_REQUIRE(codes == nullptr || n_bit <= (symmetric ? 7 : 8),
+                "group_fakequant: codes do not fit 8 bits");
+  if (N == 0) return B200Q_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GroupQuantArgs a;
+  a.maxint = (float)((1 << n_bit) - 1);
+  a.n_groups = N * (K / G);
+  a.G = G;
+  a.K = K;
+  a.colvec = colvec;
+  a.codes = codes;
+  a.scales = scales;
+  a.zeros = zeros;
+  const bool fast = (G == 128) && aligned16(W) && aligned16(out) &&
+                    (colop == B200Q_COLOP_NONE || aligned16(colvec));
+#define B200Q_GQ(SYM, OP) return launch_group_quant<T, SYM, OP>(W, out, a, fast, st)
+  B200Q_DISPATCH_DTYPE(dtype, T, {
+    if (symmetric) {
+      if (colop == B200Q_COLOP_NONE) B200Q_GQ(true, B200Q_COLOP_NONE);
+      if (colop == B200Q_COLOP_MUL_DIV) B200Q_GQ(true, B200Q_COLOP_MUL_DIV);
+      B200Q_GQ(true, B200Q_COLOP_DIV);
+    } else {
+      if (colop == B200Q_COLOP_NONE) B200Q_GQ(false, B200Q_COLOP_NONE);
+      if (colop == B200Q_COLOP_MUL_DIV) B200Q_GQ(false, B200Q_COLOP_MUL_DIV);
+      B200Q_GQ(false, B200Q_COLOP_DIV);
+    }
+  });
+#undef B200Q_GQ
+  return B200Q_OK;
+}
+
+static int promote_dtype(int a, int b) {
+  if (a == b) return a;
+  return B200Q_F32;
+}
+
+int b200q_smooth_scale(const float* act_scale, const float* wmax, float* s, int64_t K, float alpha,
+                       int act_dtype, int w_dtype, void* stream) {
+  B200Q_REQUIRE(act_scale && wmax && s && K > 0, "smooth_scale: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the reference evaluates 1.0 - alpha in Python doubles before torch narrows it
+  const float one_m_alpha = (float)(1.0 - (double)alpha);
+  smooth_scale_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(
+      act_scale, wmax, s, K, alpha, one_m_alpha, act_dtype, w_dtype,
+      promote_dtype(act_dtype, w_dtype));
+  count_launch();
+  return check_launch("smooth_scale");
+}
+
+int b200q_col_scale(const void* W, void* out, const float* s, int64_t N, int64_t K, int mul,
+                    int dtype, void* stream) {
+  B200Q_REQUIRE(W && out && s && N >= 0 && K > 0, "col_scale: bad argument");
+  if (N == 0) return B200Q_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  B200Q_DISPATCH_DTYPE(dtype, T, {
+    constexpr int VEC = ST<T>::VEC;
+    const bool vec_ok = aligned16(W) && aligned16(out) && (K % VEC == 0);
+    const int64_t cols_per_block = vec_ok ? 32 * VEC : 32;
+    const int64_t col_tiles = (K + cols_per_block - 1) / cols_per_block;
+    const int rpb = pick_rows_per_block(N, col_tiles);
+    dim3 grid((unsigned)col_tiles, (unsigned)((N + rpb - 1) / rpb));
+    const T* Wt = static_cast<const T*>(W);
+    T* Ot = static_cast<T*>(out);
+    if (vec_ok) {
+      if (mul) col_scale_kernel<T, true, true><<<grid, 256, 0, st>>>(Wt, Ot, s, N, K, rpb);
+      else col_scale_kernel<T, false, true><<<grid, 256, 0, st>>>(Wt, Ot, s, N, K, rpb);
+    } else {
+      if (mul) col_scale_kernel<T, true, false><<<grid, 256, 0, st>>>(Wt, Ot, s, N, K, rpb);
+      else col_scale_kernel<T, false, false><<<grid, 256, 0, st>>>(Wt, Ot, s, N, K, rpb);
+    }
+  });
+  count_launch();
+  return check_launch("col_scale");
+}
+
+int64_t b200q_act_stat_workspace(int64_t T, int64_t K) {
+  // one fp32 partial row per row chunk; chunks never exceed 148*8
+  (void)T;
+  return (int64_t)sizeof(float) * K * (kNumSMs * 8 + 1);
+}
+
+int b200q_act_meanabs(const void* X, int64_t T, int64_t K, int dtype, float* out, void* work,
+                      void* stream) {
+  B200Q_REQUIRE(X && out && work && T > 0 && K > 0, "act_meanabs: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  B200Q_DISPATCH_DTYPE(dtype, Tt, {
+    constexpr int VEC = ST<Tt>::VEC;
+    B200Q_REQUIRE(aligned16(X) && K % VEC == 0, "act_meanabs: K must be a multiple of 16 bytes");
+    const int64_t col_tiles = (K + 32 * VEC - 1) / (32 * VEC);
+    const int rpb = pick_rows_per_block(T, col_tiles);
+    const int chunks = (int)((T + rpb - 1) / rpb);
+    dim3 grid((unsigned)col_tiles, (unsigned)chunks);
+    act_abssum_partial_kernel<Tt><<<grid, 256, 0, st>>>(static_cast<const Tt*>(X), T, K, rpb,
+                                                        static_cast<float*>(work));
+    act_mean_finish_kernel<Tt><<<(unsigned)((K + 255) / 256), 256, 0, st>>>(
+        static_cast<const float*>(work), chunks, K, (float)T, out);
+  });
+  count_launch(2);
+  return check_launch("act_meanabs");
+}
+
+int b200q_act_maxabs(const void* X, int64_t T, int64_t K, int dtype, float* out, int accumulate,
+                     void* stream) {
+  // max|x| over tokens is the same reduction as the weight column |max|
+  return b200q_col_absmax(X, T, K, K, dtype, out, accumulate, stream);
+}
+
+int b200q_seq_sum_rows(const void* V, int64_t n, int64_t K, int dtype, float* out, void* stream) {
+  B200Q_REQUIRE(V && out && n >= 0 && K > 0, "seq_sum_rows: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  B200Q_DISPATCH_DTYPE(dtype, T,
+                       (seq_sum_rows_kernel<T><<<(unsigned)((K + 255) / 256), 256, 0, st>>>(
+                           static_cast<const T*>(V), n, K, out)));
+  count_launch();
+  return check_launch("seq_sum_rows");
+}
+
+}  // extern "C"

@@ -1,0 +1,68 @@
+"""Size-independent properties at BASELINE.json's full layer shapes (the oracle is too slow there):
+idempotence of the quantizers, code ranges, group-wise invariants, row-shard consistency."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(4096, 4096), (11008, 4096), (4096, 11008)]
+
+
+@pytest.mark.parametrize("N,K", SHAPES)
+def test_uniform_fakequant_properties(N, K):
+    from b200q import ops
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.02
+    out, codes, scales, zeros = ops.group_fakequant(w, 4, 128, return_codes=True)
+    assert codes.min() >= 0 and codes.max() <= 15
+    # dequantisation identity, exactly as the reference writes it
+    deq = (codes.float().view(-1, 128) - zeros[:, None]) * scales[:, None]
+    assert torch.equal(deq.view(N, K), out)
+    # every group's extremes are representable: error bounded by scale/2 (+ rounding)
+    assert ((out - w).abs().view(-1, 128) <= scales[:, None] * 0.5001).all()
+    # row-shard consistency: quantising a row block alone gives the same rows
+    part = ops.group_fakequant(w[1000:1500].contiguous(), 4, 128)
+    assert torch.equal(part, out[1000:1500])
+
+
+@pytest.mark.parametrize("N,K", SHAPES)
+def test_gptq_parity_properties(N, K):
+    from b200q import ops
+    g = torch.Generator(device="cuda").manual_seed(N * 3 + K)
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.02
+    out, codes, scales = ops.gptq_parity_quant(w, 4, return_codes=True)
+    assert codes.min() >= -16 and codes.max() <= 15
+    assert torch.equal(scales, (w.abs().amax(0) / 15).clamp(min=1e-5))
+    assert torch.equal(codes.float() * scales, out)
+    # idempotent: the quantized matrix is a fixed point (column max is a grid point)
+    assert torch.equal(ops.gptq_parity_quant(out, 4), out)
+    # sharded: two row halves with a max-combined column statistic reproduce the full result
+    cm = ops.col_absmax(w[: N // 2].contiguous())
+    ops.col_absmax(w[N // 2:].contiguous(), out=cm, accumulate=True)
+    top = ops.gptq_parity_quant(w[: N // 2].contiguous(), 4, colmax=cm)
+    assert torch.equal(top, out[: N // 2])
+
+
+@pytest.mark.parametrize("N,K", [(4096, 4096)])
+def test_pot_apot_properties_full_matrix(N, K):
+    from pot_apot_quantizer import pot_quantize_tensor, apot_quantize_tensor, _apot_signed_levels
+    g = torch.Generator(device="cuda").manual_seed(5)
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.02
+    q = pot_quantize_tensor(w, 4, 128)
+    # every value is +-scale*2^E: per group at most 8 distinct magnitudes (+0), ratios powers of two
+    mags = q.abs().view(-1, 128)
+    top = mags.amax(1, keepdim=True)
+    ratio = torch.where(mags > 0, top / mags, torch.ones_like(mags))
+    assert torch.equal(ratio, torch.exp2(torch.round(torch.log2(ratio))))
+    assert ratio.max() <= 128
+    assert (torch.sign(q) == torch.sign(w)).all()
+    from b200q import ops
+    lv = _apot_signed_levels(4, 2)
+    a = apot_quantize_tensor(w, 4, 128, 2)
+    out, lidx, scale, idx = ops.apot_quant(w.view(-1, 128), lv, torch.arange(0.01, 2.01, 0.1),
+                                           return_codes=True)
+    assert torch.equal(out.view(N, K), a)
+    assert lidx.max() < lv.numel() and idx.min() >= 0 and idx.max() < 20
+    assert torch.equal(scale[:, None] * lv.cuda()[lidx.long()], out)
+    # row-shard consistency for POT (APOT's grid depends on the global element count)
+    assert torch.equal(pot_quantize_tensor(w[100:164].contiguous(), 4, 128), q[100:164])
