@@ -32,7 +32,8 @@ def test_gptq_parity_properties(N, K):
     w = torch.randn(N, K, device="cuda", generator=g) * 0.02
     out, codes, scales = ops.gptq_parity_quant(w, 4, return_codes=True)
     assert codes.min() >= -16 and codes.max() <= 15
-    assert torch.equal(scales, (w.abs().amax(0) / 15).clamp(min=1e-5))
+    # (torch-on-CUDA turns `x / 15` into `x * (1/15)`; the reference semantics are the CPU's true division)
+    assert torch.equal(scales.cpu(), (w.cpu().abs().amax(0) / 15).clamp(min=1e-5))
     assert torch.equal(codes.float() * scales, out)
     # idempotent: the quantized matrix is a fixed point (column max is a grid point)
     assert torch.equal(ops.gptq_parity_quant(out, 4), out)
