@@ -174,37 +174,15 @@ DOMINANT = {"awq": "group_fakequant", "gptq": "gptq_parity_quant", "smoothquant"
             "pot": "pot_quant", "apot": "apot_quant"}
 
 
-class KernelTimer:
-    """Wraps one b200q.ops entry so that every call inside the timed steps is bracketed by CUDA
-    events on the launching stream; bytes are the algorithmic in+out bytes of the call."""
-
-    def __init__(self, ops, name):
-        self.ops, self.name, self.orig = ops, name, getattr(ops, name)
-        self.records, self.enabled = [], False
-
-    def __enter__(self):
-        def wrapped(W, *a, **kw):
-            if not self.enabled:
-                return self.orig(W, *a, **kw)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = self.orig(W, *a, **kw)
-            e1.record()
-            self.records.append((e0, e1, 2 * W.numel() * W.element_size()))
-            return out
-        setattr(self.ops, self.name, wrapped)
-        return self
-
-    def __exit__(self, *exc):
-        setattr(self.ops, self.name, self.orig)
-
-    def summary(self):
-        if not self.records:
-            return None
-        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in self.records)
-        by = sum(b for _, _, b in self.records)
-        return {"launches": len(self.records), "avg_ms": ms / len(self.records),
-                "bytes_per_launch": by / len(self.records), "gbs": by / (ms * 1e-3) / 1e9}
+def kernel_summary(_lib, name):
+    """CUDA-event time of every call of C-ABI entry point `name` recorded during the timed steps
+    (the library brackets its launches with events on the launching stream, see b200quant.h)."""
+    q = _lib.profile_query(name)
+    if q["launches"] == 0:
+        return None
+    return {"launches": q["launches"], "avg_ms": q["ms"] / q["launches"],
+            "bytes_per_launch": q["bytes"] / q["launches"],
+            "gbs": q["bytes"] / (q["ms"] * 1e-3) / 1e9 if q["ms"] > 0 else 0.0}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -336,27 +314,27 @@ def main():
         else:
             run(model)
 
-    with KernelTimer(ops, DOMINANT[args.method]) as kt:
-        for _ in range(args.warmup):
-            one_step()
-        barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
-        launches0 = _lib.launch_count()
-        kt.enabled = True
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            one_step()
-        e1.record()
-        barrier()
-        kt.enabled = False
-        ms_total = e0.elapsed_time(e1)
-        launches = _lib.launch_count() - launches0
-        clocks = sampler.stop() if rank == 0 else None
-        ksum = kt.summary()
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    _lib.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        one_step()
+    e1.record()
+    barrier()
+    _lib.profile_enable(False)
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ksum = kernel_summary(_lib, DOMINANT[args.method])
+    kall = _lib.profile_query(None)
 
     t = torch.tensor([ms_total], dtype=torch.float64, device=device)
     if world > 1:
@@ -408,6 +386,7 @@ def main():
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "clocks": clocks,
         "hbm_gbs_whole_step": 2 * local_bytes / (ms_step * 1e-3) / 1e9,
+        "kernel_ms_per_step": kall["ms"] / args.steps,
     }
     print(json.dumps(line))
     if world > 1:

@@ -49,6 +49,16 @@ int b200q_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t b200q_launch_count(void);
 
+/* ---- in-library kernel timing ---------------------------------------------------------
+ * b200q_profile_enable(1) clears old records and makes every following entry point bracket
+ * its launches with two CUDA events on the launching stream; (0) stops recording.
+ * b200q_profile_query sums, for the entry point called `name` ("group_fakequant", "pot_quant",
+ * ...; NULL = all), the device time, launch count and the ALGORITHMIC bytes / flops the calls
+ * declared.  It waits for the recorded events. */
+void b200q_profile_enable(int on);
+int b200q_profile_query(const char* name, double* total_ms, int64_t* launches, double* bytes,
+                        double* flops);
+
 /* ---- torch-CPU log2 semantics, exported for the CPU test-suite -------------------
  * rne(log2f(r)) and floor(log2f(m)) as torch's CPU kernel evaluates them are step
  * functions of r; the library tabulates the step positions on the host at load
@@ -105,6 +115,32 @@ int b200q_act_maxabs(const void* X, int64_t T, int64_t K, int dtype, float* out,
 /* out[k] = ((0 + V[0,k]) + V[1,k]) + ... sequential, each partial sum rounded to V's dtype: the
  * order and precision of Python's sum() over a list of [K] tensors.   ref: awq_quantizer.py:57 */
 int b200q_seq_sum_rows(const void* V, int64_t n, int64_t K, int dtype, float* out, void* stream);
+
+/* colmul[i] = factor for the k largest entries of importance[K] (ties at the k-th value taken
+ * in index order), 1 elsewhere; mask (uint8 [K], optional) flags them.
+ * ref: awq_quantizer.py:60-61 (torch.topk) feeding :70,:81 */
+int b200q_topk_colmul(const float* importance, int64_t K, int64_t k, float factor, float* colmul,
+                      uint8_t* mask, void* stream);
+
+/* ---- whole-layer entry points --------------------------------------------------------
+ * One host call per nn.Linear: the per-layer launch sequence of a model walker, so that
+ * host overhead stays below the kernels' HBM time.  `work` is device scratch of 2*K floats.
+ *   awq_layer:        feats [n_feats,K] -> importance -> top n_protect -> fused scale/quant/unscale
+ *                     ref: awq_quantizer.py:56-84
+ *   gptq_parity_layer: column |max| (into colmax[K]) -> column quantisation
+ *                     ref: gptq_quantizer.py:167-206 (single GPU; row shards all-reduce colmax
+ *                     between b200q_col_absmax and b200q_gptq_parity_quant instead)
+ *   smoothquant_layer: column |max| -> s[K] -> fused W/s + group fake-quant
+ *                     ref: smooth_quant_quantizer.py:150-170,313 */
+int b200q_awq_layer(const void* W, void* out, int64_t N, int64_t K, int64_t group, int n_bit,
+                    const void* feats, int64_t n_feats, int feat_dtype, int64_t n_protect,
+                    float scale_factor, float* work, uint8_t* salient_mask, int dtype,
+                    void* stream);
+int b200q_gptq_parity_layer(const void* W, void* out, int64_t N, int64_t K, int n_bit,
+                            float* colmax, int dtype, void* stream);
+int b200q_smoothquant_layer(const void* W, void* out, int64_t N, int64_t K, int64_t group,
+                            int n_bit, const float* act_scale, float alpha, int act_dtype,
+                            float* s, float* work, int dtype, void* stream);
 
 /* ---- POT ------------------------------------------------------------------------------
  * ref: pot_apot_quantizer.py:25-115.  w is [n_groups, group] contiguous; grid_host is the

@@ -30,13 +30,21 @@ from quantization_utils import pseudo_quantize_tensor  # noqa: E402,F401  (re-ex
 SEARCH_STUB = False
 
 
-def _importance(feats: List[torch.Tensor], device) -> torch.Tensor:
-    """sum(list of [K] tensors).float(), evaluated left to right in the tensors' own dtype."""
-    if isinstance(feats, torch.Tensor):       # an [n, K] tensor iterates (and sums) row by row
+def _feat_matrix(feats, device) -> torch.Tensor:
+    """The per-batch statistics of one layer as an [n, K] matrix on `device`.  The reference takes
+    a list of [K] tensors; an [n, K] tensor iterates (and sums) row by row and is accepted as is."""
+    if isinstance(feats, torch.Tensor):
         stacked = feats.reshape(feats.shape[0], -1)
     else:
         stacked = torch.stack([f.reshape(-1) for f in feats])
-    return _ops.seq_sum_rows(stacked.to(device, non_blocking=True))
+    if stacked.dtype not in _ops.DTYPE_CODE:
+        stacked = stacked.float()
+    return stacked.to(device, non_blocking=True)
+
+
+def _importance(feats, device) -> torch.Tensor:
+    """sum(list of [K] tensors).float(), evaluated left to right in the tensors' own dtype."""
+    return _ops.seq_sum_rows(_feat_matrix(feats, device))
 
 
 def _salient_channels(importance: torch.Tensor, protect_ratio: float) -> torch.Tensor:
@@ -56,13 +64,13 @@ def awq_quantize_model_weight(
     """AWQ-protect and fake-quantize every calibrated nn.Linear in place; Linears without
     calibration features are left untouched (reference: awq_quantizer.py:50-54)."""
     def compute(name, _module, W):
+        K = W.shape[-1]
         if q_group_size > 0:
-            assert W.shape[-1] % q_group_size == 0
-        salient = _salient_channels(_importance(input_feat[name], W.device), protect_ratio)
-        assert salient.dim() == 1
-        colmul = torch.ones(W.shape[1], dtype=torch.float32, device=W.device)
-        colmul[salient] = float(scale_factor)
-        return _ops.group_fakequant(W, w_bit, q_group_size, colop=_ops.COLOP_MUL_DIV, colvec=colmul)
+            assert K % q_group_size == 0
+        # importance sum, top-k and the fused scale/quantize/unscale pass: one host call
+        n_protect = max(1, int(K * protect_ratio))
+        return _ops.awq_layer(W, _feat_matrix(input_feat[name], W.device), w_bit, q_group_size,
+                              n_protect, scale_factor)
 
     _pipeline.run_layers([(n, m) for n, m in model.named_modules()
                           if isinstance(m, nn.Linear) and n in input_feat], compute)

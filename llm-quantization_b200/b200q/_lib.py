@@ -37,6 +37,15 @@ SIGNATURES = {
     "b200q_act_meanabs": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_fp, c_vp, c_vp]),
     "b200q_act_maxabs": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_fp, C.c_int, c_vp]),
     "b200q_seq_sum_rows": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_fp, c_vp]),
+    "b200q_profile_enable": (None, [C.c_int]),
+    "b200q_profile_query": (C.c_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(c_i64),
+                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "b200q_topk_colmul": (C.c_int, [c_fp, c_i64, c_i64, C.c_float, c_fp, c_vp, c_vp]),
+    "b200q_awq_layer": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp, c_i64, C.c_int,
+                                  c_i64, C.c_float, c_fp, c_vp, C.c_int, c_vp]),
+    "b200q_gptq_parity_layer": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_fp, C.c_int, c_vp]),
+    "b200q_smoothquant_layer": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_int, c_fp, C.c_float,
+                                          C.c_int, c_fp, c_fp, C.c_int, c_vp]),
     "b200q_pot_quant": (C.c_int, [c_vp, c_vp, c_vp, c_fp, c_vp, c_i64, c_i64, C.c_int,
                                   C.POINTER(C.c_float), C.c_int, C.c_int, c_vp]),
     "b200q_apot_quant": (C.c_int, [c_vp, c_vp, c_vp, c_fp, c_vp, c_i64, c_i64,
@@ -86,3 +95,16 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(load().b200q_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    load().b200q_profile_enable(int(on))
+
+
+def profile_query(name=None):
+    """{'ms','launches','bytes','flops'} summed over the recorded calls of entry point `name`."""
+    ms, n, by, fl = C.c_double(), c_i64(), C.c_double(), C.c_double()
+    rc = load().b200q_profile_query(None if name is None else name.encode(), C.byref(ms),
+                                    C.byref(n), C.byref(by), C.byref(fl))
+    check(rc, "profile_query")
+    return {"ms": ms.value, "launches": n.value, "bytes": by.value, "flops": fl.value}

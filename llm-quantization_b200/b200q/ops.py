@@ -237,3 +237,74 @@ def apot_quant(w: torch.Tensor, levels: torch.Tensor, grid: torch.Tensor,
                                           dtype_code(w), _stream())
     _lib.check(rc, "apot_quant")
     return (out, lidx, scale, idx) if return_codes else out
+
+
+# --------------------------------------------------------------------------------------------------
+# whole-layer calls: one host call per nn.Linear
+# --------------------------------------------------------------------------------------------------
+_scratch = {}
+
+
+def _work(device, n_floats: int) -> torch.Tensor:
+    """Per-device fp32 scratch, grown on demand (stream-ordered reuse on the current stream)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < n_floats:
+        buf = torch.empty(max(n_floats, 1 << 16), dtype=torch.float32, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+def awq_layer(W: torch.Tensor, feats: torch.Tensor, n_bit: int, group: int, n_protect: int,
+              scale_factor: float, return_mask: bool = False):
+    """importance -> top-k -> fused scale / asymmetric group fake-quant / unscale of a CUDA [N,K]
+    weight; feats is a CUDA [n,K] matrix of per-batch mean|x| rows."""
+    assert W.is_cuda and W.dim() == 2 and feats.is_cuda and feats.dim() == 2
+    W = W.contiguous()
+    feats = feats.contiguous()
+    N, K = W.shape
+    assert feats.shape[1] == K
+    out = torch.empty_like(W)
+    mask = torch.empty(K, dtype=torch.uint8, device=W.device) if return_mask else None
+    with torch.cuda.device(W.device):
+        work = _work(W.device, 2 * K)
+        rc = _lib.load().b200q_awq_layer(W.data_ptr(), out.data_ptr(), N, K, group, n_bit,
+                                         feats.data_ptr(), feats.shape[0], dtype_code(feats),
+                                         n_protect, float(scale_factor), work.data_ptr(), _ptr(mask),
+                                         dtype_code(W), _stream())
+    _lib.check(rc, "awq_layer")
+    return (out, mask) if return_mask else out
+
+
+def gptq_parity_layer(W: torch.Tensor, n_bit: int) -> torch.Tensor:
+    assert W.is_cuda and W.dim() == 2
+    W = W.contiguous()
+    N, K = W.shape
+    out = torch.empty_like(W)
+    with torch.cuda.device(W.device):
+        work = _work(W.device, K)
+        rc = _lib.load().b200q_gptq_parity_layer(W.data_ptr(), out.data_ptr(), N, K, n_bit,
+                                                 work.data_ptr(), dtype_code(W), _stream())
+    _lib.check(rc, "gptq_parity_layer")
+    return out
+
+
+def smoothquant_layer(W: torch.Tensor, act_scale: torch.Tensor, alpha: float, n_bit: int,
+                      group: int):
+    """(quantized smoothed weight, s fp32 [K]) for a CUDA [N,K] weight and fp32/16 act_scale [K]
+    of the same dtype family as W (mixed dtypes go through the separate calls)."""
+    assert W.is_cuda and W.dim() == 2
+    W = W.contiguous()
+    N, K = W.shape
+    a = _f32(act_scale, W.device)
+    assert a.numel() == K, "act_scales length does not match in_features"
+    out = torch.empty_like(W)
+    s = torch.empty(K, dtype=torch.float32, device=W.device)
+    with torch.cuda.device(W.device):
+        work = _work(W.device, K)
+        rc = _lib.load().b200q_smoothquant_layer(W.data_ptr(), out.data_ptr(), N, K, group, n_bit,
+                                                 a.data_ptr(), float(alpha),
+                                                 DTYPE_CODE.get(act_scale.dtype, 0), s.data_ptr(),
+                                                 work.data_ptr(), dtype_code(W), _stream())
+    _lib.check(rc, "smoothquant_layer")
+    return out, s

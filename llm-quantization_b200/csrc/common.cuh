@@ -22,6 +22,21 @@ int fail(int code, const std::string& msg);
 void count_launch(int n = 1);
 int check_launch(const char* what);
 
+// Brackets the launches of one C-ABI call with CUDA events when profiling is on (core.cu).
+class KernelScope {
+ public:
+  KernelScope(const char* name, double bytes, double flops, cudaStream_t st);
+  ~KernelScope();
+  KernelScope(const KernelScope&) = delete;
+  KernelScope& operator=(const KernelScope&) = delete;
+
+ private:
+  const char* name_;
+  double bytes_, flops_;
+  cudaStream_t st_;
+  cudaEvent_t e0_, e1_;
+};
+
 #define B200Q_REQUIRE(cond, msg)                                 \
   do {                                                           \
     if (!(cond)) return ::b200q::fail(B200Q_EINVAL, (msg));      \

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -23,6 +24,36 @@ int check_launch(const char* what) {
     return fail(B200Q_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
   }
   return B200Q_OK;
+}
+
+// ---- per-entry-point CUDA-event profiler --------------------------------------------------------
+// bench.py turns this on for the timed steps: every C-ABI call then brackets its launches with two
+// events on the launching stream, so kernel durations are measured inside the real pipeline rather
+// than in a separate replay.  Off by default (two relaxed loads per call).
+struct ProfRec {
+  const char* name;
+  cudaEvent_t e0, e1;
+  double bytes, flops;
+};
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+
+KernelScope::KernelScope(const char* name, double bytes, double flops, cudaStream_t st)
+    : name_(name), bytes_(bytes), flops_(flops), st_(st), e0_(nullptr), e1_(nullptr) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  if (cudaEventCreate(&e0_) != cudaSuccess || cudaEventCreate(&e1_) != cudaSuccess) {
+    e0_ = e1_ = nullptr;
+    cudaGetLastError();
+    return;
+  }
+  cudaEventRecord(e0_, st_);
+}
+KernelScope::~KernelScope() {
+  if (e0_ == nullptr) return;
+  cudaEventRecord(e1_, st_);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_prof.push_back({name_, e0_, e1_, bytes_, flops_});
 }
 
 // ---- torch-CPU log2 semantics ------------------------------------------------------------------
@@ -82,6 +113,38 @@ extern "C" {
 const char* b200q_last_error(void) { return b200q::g_last_error.c_str(); }
 int b200q_version(void) { return 100; }
 int64_t b200q_launch_count(void) { return b200q::g_launches.load(); }
+
+void b200q_profile_enable(int on) {
+  std::lock_guard<std::mutex> lock(b200q::g_prof_mu);
+  if (on) {
+    for (auto& r : b200q::g_prof) {
+      cudaEventDestroy(r.e0);
+      cudaEventDestroy(r.e1);
+    }
+    b200q::g_prof.clear();
+  }
+  b200q::g_prof_on.store(on != 0);
+}
+
+int b200q_profile_query(const char* name, double* total_ms, int64_t* launches, double* bytes,
+                        double* flops) {
+  std::lock_guard<std::mutex> lock(b200q::g_prof_mu);
+  double ms = 0, by = 0, fl = 0;
+  int64_t n = 0;
+  for (auto& r : b200q::g_prof) {
+    if (name != nullptr && std::strcmp(name, r.name) != 0) continue;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) return b200q::fail(B200Q_ECUDA, "profile: sync");
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess)
+      return b200q::fail(B200Q_ECUDA, "profile: elapsed");
+    ms += t; by += r.bytes; fl += r.flops; ++n;
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = n;
+  if (bytes) *bytes = by;
+  if (flops) *flops = fl;
+  return B200Q_OK;
+}
 
 uint32_t b200q_log2_round_threshold_bits(int e) {
   if (e < -127 || e > 127) return 0;

@@ -539,6 +539,72 @@ __global__ void seq_sum_rows_kernel(const T* __restrict__ V, int64_t n, int64_t 
   out[k] = v;
 }
 
+// =================================================================================================
+// top-k channel mask (ref: awq_quantizer.py:60-61  torch.topk(importance, n_protect))
+// =================================================================================================
+// One CTA: 4-pass MSB radix select over the order-preserving uint image of the floats finds the
+// k-th largest value; everything above it is salient, ties at the threshold are taken in index
+// order.  Writes colmul[i] = (salient ? factor : 1) and, optionally, a uint8 mask.
+__device__ __forceinline__ uint32_t ordered_bits(float x) {
+  const uint32_t b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(1024)
+topk_colmul_kernel(const float* __restrict__ v, int K, int k, float factor,
+                   float* __restrict__ colmul, uint8_t* __restrict__ mask) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int s_prefix, s_need, s_eq_base[1024];
+  const int tid = threadIdx.x;
+  if (tid == 0) { s_prefix = 0; s_need = (unsigned)k; }
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    const uint32_t pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = tid; i < K; i += blockDim.x) {
+      const uint32_t u = ordered_bits(v[i]);
+      if ((u & pmask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned need = s_need;
+      int b = 255;
+      for (; b > 0; --b) {
+        if (hist[b] >= need) break;
+        need -= hist[b];
+      }
+      s_need = need;                       // how many still to take inside bin b
+      s_prefix = prefix | ((uint32_t)b << shift);
+    }
+    __syncthreads();
+  }
+  const uint32_t thr = s_prefix;           // exact bits of the k-th largest value
+  const unsigned need_eq = s_need;         // number of elements == thr to accept (index order)
+  // contiguous chunk per thread so that "index order" is a prefix sum over threads
+  const int per = (K + blockDim.x - 1) / blockDim.x;
+  const int i0 = tid * per, i1 = min(K, i0 + per);
+  unsigned eq = 0;
+  for (int i = i0; i < i1; ++i) eq += (ordered_bits(v[i]) == thr);
+  s_eq_base[tid] = eq;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned run = 0;
+    for (int t = 0; t < blockDim.x; ++t) { const unsigned c = s_eq_base[t]; s_eq_base[t] = run; run += c; }
+  }
+  __syncthreads();
+  unsigned seen = s_eq_base[tid];
+  for (int i = i0; i < i1; ++i) {
+    const uint32_t u = ordered_bits(v[i]);
+    bool take = u > thr;
+    if (u == thr) { take = seen < need_eq; ++seen; }
+    colmul[i] = take ? factor : 1.f;
+    if (mask != nullptr) mask[i] = take ? 1 : 0;
+  }
+}
+
 }  // namespace b200q
 
 // =================================================================================================
@@ -557,6 +623,7 @@ int b200q_col_absmax(const void* W, int64_t N, int64_t K, int64_t ld, int dtype,
     if (!accumulate) cudaMemsetAsync(colmax, 0, sizeof(float) * K, st);
     return B200Q_OK;
   }
+  KernelScope scope("col_absmax", (double)N * K * elem_size(dtype), 0, st);
   B200Q_DISPATCH_DTYPE(dtype, T, return launch_col_absmax<T>(W, N, K, ld, colmax, accumulate, st));
   return B200Q_OK;
 }
@@ -571,6 +638,7 @@ int b200q_gptq_parity_quant(const void* W, void* out, int8_t* codes, const float
   if (N == 0) return B200Q_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float maxint = (float)((1 << n_bit) - 1);
+  KernelScope scope("gptq_parity_quant", 2.0 * N * K * elem_size(dtype), 0, st);
   B200Q_DISPATCH_DTYPE(dtype, T, {
     constexpr int VEC = ST<T>::VEC;
     const bool vec_ok = aligned16(W) && aligned16(out) && (K % VEC == 0) && (ld % VEC == 0);
@@ -617,6 +685,7 @@ int b200q_group_fakequant(const void* W, void* out, void* codes, float* scales, 
   a.zeros = zeros;
   const bool fast = (G == 128) && aligned16(W) && aligned16(out) &&
                     (colop == B200Q_COLOP_NONE || aligned16(colvec));
+  KernelScope scope("group_fakequant", 2.0 * N * K * elem_size(dtype), 0, st);
 #define B200Q_GQ(SYM, OP) return launch_group_quant<T, SYM, OP>(W, out, a, fast, st)
   B200Q_DISPATCH_DTYPE(dtype, T, {
     if (symmetric) {
@@ -656,6 +725,7 @@ int b200q_col_scale(const void* W, void* out, const float* s, int64_t N, int64_t
   B200Q_REQUIRE(W && out && s && N >= 0 && K > 0, "col_scale: bad argument");
   if (N == 0) return B200Q_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KernelScope scope("col_scale", 2.0 * N * K * elem_size(dtype), 0, st);
   B200Q_DISPATCH_DTYPE(dtype, T, {
     constexpr int VEC = ST<T>::VEC;
     const bool vec_ok = aligned16(W) && aligned16(out) && (K % VEC == 0);
@@ -687,6 +757,7 @@ int b200q_act_meanabs(const void* X, int64_t T, int64_t K, int dtype, float* out
                       void* stream) {
   B200Q_REQUIRE(X && out && work && T > 0 && K > 0, "act_meanabs: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KernelScope scope("act_meanabs", (double)T * K * elem_size(dtype), 0, st);
   B200Q_DISPATCH_DTYPE(dtype, Tt, {
     constexpr int VEC = ST<Tt>::VEC;
     B200Q_REQUIRE(aligned16(X) && K % VEC == 0, "act_meanabs: K must be a multiple of 16 bytes");
@@ -717,6 +788,51 @@ int b200q_seq_sum_rows(const void* V, int64_t n, int64_t K, int dtype, float* ou
                            static_cast<const T*>(V), n, K, out)));
   count_launch();
   return check_launch("seq_sum_rows");
+}
+
+int b200q_topk_colmul(const float* importance, int64_t K, int64_t k, float factor, float* colmul,
+                      uint8_t* mask, void* stream) {
+  B200Q_REQUIRE(importance && colmul && K > 0 && k >= 0 && k <= K && K < (1ll << 30),
+                "topk_colmul: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  topk_colmul_kernel<<<1, 1024, 0, st>>>(importance, (int)K, (int)k, factor, colmul, mask);
+  count_launch();
+  return check_launch("topk_colmul");
+}
+
+// ---- whole-layer entry points: every launch of one Linear behind ONE host call ----------------
+int b200q_awq_layer(const void* W, void* out, int64_t N, int64_t K, int64_t group, int n_bit,
+                    const void* feats, int64_t n_feats, int feat_dtype, int64_t n_protect,
+                    float scale_factor, float* work, uint8_t* salient_mask, int dtype,
+                    void* stream) {
+  B200Q_REQUIRE(feats && work && n_feats > 0, "awq_layer: bad argument");
+  float* importance = work;      // [K]
+  float* colmul = work + K;      // [K]
+  int rc = b200q_seq_sum_rows(feats, n_feats, K, feat_dtype, importance, stream);
+  if (rc != B200Q_OK) return rc;
+  rc = b200q_topk_colmul(importance, K, n_protect, scale_factor, colmul, salient_mask, stream);
+  if (rc != B200Q_OK) return rc;
+  return b200q_group_fakequant(W, out, nullptr, nullptr, nullptr, N, K, group, n_bit, 0,
+                               B200Q_COLOP_MUL_DIV, colmul, dtype, stream);
+}
+
+int b200q_gptq_parity_layer(const void* W, void* out, int64_t N, int64_t K, int n_bit,
+                            float* colmax, int dtype, void* stream) {
+  int rc = b200q_col_absmax(W, N, K, K, dtype, colmax, 0, stream);
+  if (rc != B200Q_OK) return rc;
+  return b200q_gptq_parity_quant(W, out, nullptr, colmax, nullptr, N, K, K, n_bit, dtype, stream);
+}
+
+int b200q_smoothquant_layer(const void* W, void* out, int64_t N, int64_t K, int64_t group,
+                            int n_bit, const float* act_scale, float alpha, int act_dtype,
+                            float* s, float* work, int dtype, void* stream) {
+  B200Q_REQUIRE(act_scale && s && work, "smoothquant_layer: bad argument");
+  int rc = b200q_col_absmax(W, N, K, K, dtype, work, 0, stream);
+  if (rc != B200Q_OK) return rc;
+  rc = b200q_smooth_scale(act_scale, work, s, K, alpha, act_dtype, dtype, stream);
+  if (rc != B200Q_OK) return rc;
+  return b200q_group_fakequant(W, out, nullptr, nullptr, nullptr, N, K, group, n_bit, 0,
+                               B200Q_COLOP_DIV, s, dtype, stream);
 }
 
 }  // extern "C"

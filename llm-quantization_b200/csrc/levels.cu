@@ -427,6 +427,7 @@ int b200q_pot_quant(const void* w, void* out, uint8_t* exps, float* best_scale, 
   int rc = ensure_tables_uploaded();
   if (rc != B200Q_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KernelScope scope("pot_quant", 2.0 * n_groups * group * elem_size(dtype), 0, st);
   PotConsts c;
   c.emax_idx = (1 << (n_bit - 1)) - 1;
   c.tiny = 1.17549435e-38f;
@@ -459,6 +460,7 @@ int b200q_apot_quant(const void* w, void* out, uint8_t* level_idx, float* best_s
     return fail(B200Q_EUNSUPPORTED, "apot_quant: only fp32 weights are implemented");
   if (n_groups == 0) return B200Q_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KernelScope scope("apot_quant", 2.0 * n_groups * group * elem_size(dtype), 0, st);
   LevelParam lp;
   bool sorted = true;
   float min_gap = INFINITY;

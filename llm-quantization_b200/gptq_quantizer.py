@@ -131,8 +131,12 @@ def _gptq_device(W: torch.Tensor, n_bit: int, q_group_size: int, input_feat, per
     elif MODE == "parity":
         # The reference's loop rounds column j with s_j = clamp(max_i |W[i,j]| / (2^b-1), 1e-5) and
         # writes q*s back; permuting and un-permuting independent columns is the identity.
-        colmax = _dist.allreduce_max(_ops.col_absmax(W))   # no-op outside a row-sharded run
-        out = _ops.gptq_parity_quant(W, n_bit, colmax)
+        if _dist.is_sharded():
+            # the column scale spans ALL rows (:182): combine the shards' column maxima first
+            colmax = _dist.allreduce_max(_ops.col_absmax(W))
+            out = _ops.gptq_parity_quant(W, n_bit, colmax)
+        else:
+            out = _ops.gptq_parity_layer(W, n_bit)          # both kernels behind one host call
     else:
         raise ValueError(f"gptq_quantizer.MODE must be 'parity' or 'compensated', got {MODE!r}")
     return out

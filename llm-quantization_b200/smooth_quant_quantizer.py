@@ -171,7 +171,14 @@ def smoothquant_quantize_model_weight(model: nn.Module, w_bit: int, q_group_size
         if q_group_size > 0:
             assert W.shape[-1] % q_group_size == 0
         if name in act_scales:
-            s, s_dtype = _layer_smoothing_scale(W, act_scales[name], alpha)
+            act = act_scales[name]
+            if not _dist.is_sharded() and torch.promote_types(act.dtype, W.dtype) == W.dtype \
+                    and act.dtype in _ops.DTYPE_CODE:
+                # column |max| -> s -> fused (W / s, group fake-quant): one host call
+                out, s = _ops.smoothquant_layer(W, act, alpha, w_bit, q_group_size)
+                _attach(m, s.to(W.dtype).to(m.weight.device))
+                return out
+            s, s_dtype = _layer_smoothing_scale(W, act, alpha)
             _attach(m, s.to(s_dtype).to(m.weight.device))
             return _ops.group_fakequant(W.to(s_dtype), w_bit, q_group_size, colop=_ops.COLOP_DIV,
                                         colvec=s)

@@ -273,6 +273,46 @@ def test_importance_sum_is_pythons_left_to_right():
     assert torch.equal(_importance(feats16, "cuda").cpu(), sum(feats16).float())
 
 
+@pytest.mark.parametrize("K,k", [(4096, 40), (11008, 110), (768, 7), (130, 1), (28672, 286), (64, 64)])
+def test_topk_mask_matches_torch_topk(K, k):
+    """The radix-select top-k picks the same channel SET as torch.topk (awq_quantizer.py:61)."""
+    from b200q import ops
+    g = torch.Generator().manual_seed(K + k)
+    w = torch.randn(256, K, generator=g) * 0.02
+    chan = torch.ones(K)
+    chan[torch.randperm(K, generator=g)[: max(1, K // 100)]] = 20.0
+    feats = torch.stack([(torch.randn(16, K, generator=g) * chan).abs().mean(0) for _ in range(8)])
+    out, mask = ops.awq_layer(w.cuda(), feats.cuda(), 4, -1 if K % 128 else 128, k, 2.0,
+                              return_mask=True)
+    want = torch.zeros(K, dtype=torch.uint8)
+    want[torch.topk(sum(feats).float(), k)[1]] = 1
+    assert torch.equal(mask.cpu(), want)
+    assert int(mask.sum()) == k
+
+
+def test_topk_ties_take_lowest_indices():
+    from b200q import ops
+    feats = torch.ones(1, 256)
+    feats[0, 100] = 5.0
+    w = torch.randn(8, 256)
+    _, mask = ops.awq_layer(w.cuda(), feats.cuda(), 4, 128, 4, 2.0, return_mask=True)
+    assert mask.cpu().nonzero().flatten().tolist() == [0, 1, 2, 100]
+
+
+def test_profile_records_entry_points():
+    from b200q import _lib, ops
+    w = torch.randn(256, 1024, device="cuda")
+    _lib.profile_enable(True)
+    for _ in range(3):
+        ops.group_fakequant(w, 4, 128)
+    ops.col_absmax(w)
+    _lib.profile_enable(False)
+    q = _lib.profile_query("group_fakequant")
+    assert q["launches"] == 3 and q["ms"] > 0 and q["bytes"] == 3 * 2 * w.numel() * 4
+    assert _lib.profile_query("col_absmax")["launches"] == 1
+    assert _lib.profile_query(None)["launches"] == 4
+
+
 def test_shape_errors_are_assertions():
     from quantization_utils import pseudo_quantize_tensor
     with pytest.raises(AssertionError):
