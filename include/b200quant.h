@@ -59,6 +59,11 @@ void b200q_profile_enable(int on);
 int b200q_profile_query(const char* name, double* total_ms, int64_t* launches, double* bytes,
                         double* flops);
 
+/* Device self-test of the exact reused-divisor division the fake-quant kernels use (reciprocal
+ * + two Markstein FMA corrections) against __fdiv_rn on ~n_quotients random and adversarial
+ * pairs.  *mismatches must come back 0.  Synchronises the stream. */
+int b200q_selftest_div(int64_t n_quotients, uint64_t seed, int64_t* mismatches, void* stream);
+
 /* ---- torch-CPU log2 semantics, exported for the CPU test-suite -------------------
  * rne(log2f(r)) and floor(log2f(m)) as torch's CPU kernel evaluates them are step
  * functions of r; the library tabulates the step positions on the host at load
@@ -124,7 +129,7 @@ int b200q_topk_colmul(const float* importance, int64_t K, int64_t k, float facto
 
 /* ---- whole-layer entry points --------------------------------------------------------
  * One host call per nn.Linear: the per-layer launch sequence of a model walker, so that
- * host overhead stays below the kernels' HBM time.  `work` is device scratch of 2*K floats.
+ * host overhead stays below the kernels' HBM time.  `work` is device scratch of 3*K floats.
  *   awq_layer:        feats [n_feats,K] -> importance -> top n_protect -> fused scale/quant/unscale
  *                     ref: awq_quantizer.py:56-84
  *   gptq_parity_layer: column |max| (into colmax[K]) -> column quantisation

@@ -44,6 +44,25 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def _on(device):
+    """Device guard that costs nothing when `device` is already current (the per-layer calls of a
+    model walker are host-overhead sensitive: ~80 us/layer of Python dwarfs a 20 us kernel)."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NULL
+    return torch.cuda.device(device)
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -61,7 +80,7 @@ def col_absmax(W: torch.Tensor, out: Optional[torch.Tensor] = None,
     if out is None:
         out = torch.empty(K, dtype=torch.float32, device=W.device)
         accumulate = False
-    with torch.cuda.device(W.device):
+    with _on(W.device):
         rc = _lib.load().b200q_col_absmax(W.data_ptr(), N, K, W.stride(0) if N > 1 else K,
                                           dtype_code(W), out.data_ptr(), int(accumulate), _stream())
     _lib.check(rc, "col_absmax")
@@ -80,7 +99,7 @@ def gptq_parity_quant(W: torch.Tensor, n_bit: int, colmax: Optional[torch.Tensor
     out = torch.empty_like(W)
     codes = torch.empty((N, K), dtype=torch.int8, device=W.device) if return_codes else None
     scales = torch.empty(K, dtype=torch.float32, device=W.device) if return_codes else None
-    with torch.cuda.device(W.device):
+    with _on(W.device):
         rc = _lib.load().b200q_gptq_parity_quant(W.data_ptr(), out.data_ptr(), _ptr(codes),
                                                  colmax.data_ptr(), _ptr(scales), N, K, K, n_bit,
                                                  dtype_code(W), _stream())
@@ -107,7 +126,7 @@ def group_fakequant(W: torch.Tensor, n_bit: int, group: int, symmetric: bool = F
     if colvec is not None:
         colvec = _f32(colvec, W.device)
         assert colvec.numel() == K
-    with torch.cuda.device(W.device):
+    with _on(W.device):
         rc = _lib.load().b200q_group_fakequant(W.data_ptr(), out.data_ptr(), _ptr(codes),
                                                _ptr(scales), _ptr(zeros), N, K, group, n_bit,
                                                int(symmetric), colop, _ptr(colvec), dtype_code(W),
@@ -123,7 +142,7 @@ def smooth_scale(act_scale: torch.Tensor, wmax: torch.Tensor, alpha: float, act_
     a = _f32(act_scale, wmax.device)
     assert a.numel() == K, "act_scales length does not match in_features"
     s = torch.empty(K, dtype=torch.float32, device=wmax.device)
-    with torch.cuda.device(wmax.device):
+    with _on(wmax.device):
         rc = _lib.load().b200q_smooth_scale(a.data_ptr(), wmax.data_ptr(), s.data_ptr(), K,
                                             float(alpha), DTYPE_CODE[act_dtype], DTYPE_CODE[w_dtype],
                                             _stream())
@@ -138,7 +157,7 @@ def col_scale(W: torch.Tensor, s: torch.Tensor, mul: bool = False) -> torch.Tens
     N, K = W.shape
     s = _f32(s, W.device)
     out = torch.empty_like(W)
-    with torch.cuda.device(W.device):
+    with _on(W.device):
         rc = _lib.load().b200q_col_scale(W.data_ptr(), out.data_ptr(), s.data_ptr(), N, K, int(mul),
                                          dtype_code(W), _stream())
     _lib.check(rc, "col_scale")
@@ -154,7 +173,7 @@ def act_meanabs(X: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty(K, dtype=torch.float32, device=X.device)
     work = torch.empty(lib.b200q_act_stat_workspace(T, K), dtype=torch.uint8, device=X.device)
-    with torch.cuda.device(X.device):
+    with _on(X.device):
         rc = lib.b200q_act_meanabs(X.data_ptr(), T, K, dtype_code(X), out.data_ptr(),
                                    work.data_ptr(), _stream())
     _lib.check(rc, "act_meanabs")
@@ -170,7 +189,7 @@ def act_maxabs(X: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Ten
     accumulate = out is not None
     if out is None:
         out = torch.empty(K, dtype=torch.float32, device=X.device)
-    with torch.cuda.device(X.device):
+    with _on(X.device):
         rc = _lib.load().b200q_act_maxabs(X.data_ptr(), T, K, dtype_code(X), out.data_ptr(),
                                           int(accumulate), _stream())
     _lib.check(rc, "act_maxabs")
@@ -184,7 +203,7 @@ def seq_sum_rows(V: torch.Tensor) -> torch.Tensor:
     V = V.contiguous()
     n, K = V.shape
     out = torch.empty(K, dtype=torch.float32, device=V.device)
-    with torch.cuda.device(V.device):
+    with _on(V.device):
         rc = _lib.load().b200q_seq_sum_rows(V.data_ptr(), n, K, dtype_code(V), out.data_ptr(),
                                             _stream())
     _lib.check(rc, "seq_sum_rows")
@@ -209,7 +228,7 @@ def pot_quant(w: torch.Tensor, n_bit: int, grid: torch.Tensor, return_codes: boo
         scale = torch.empty(n_groups, dtype=torch.float32, device=w.device)
         idx = torch.empty(n_groups, dtype=torch.int32, device=w.device)
     garr, n_grid = _host_floats(grid)
-    with torch.cuda.device(w.device):
+    with _on(w.device):
         rc = _lib.load().b200q_pot_quant(w.data_ptr(), out.data_ptr(), _ptr(exps), _ptr(scale),
                                          _ptr(idx), n_groups, G, n_bit, garr, n_grid,
                                          dtype_code(w), _stream())
@@ -231,7 +250,7 @@ def apot_quant(w: torch.Tensor, levels: torch.Tensor, grid: torch.Tensor,
         idx = torch.empty(n_groups, dtype=torch.int32, device=w.device)
     larr, n_levels = _host_floats(levels)
     garr, n_grid = _host_floats(grid)
-    with torch.cuda.device(w.device):
+    with _on(w.device):
         rc = _lib.load().b200q_apot_quant(w.data_ptr(), out.data_ptr(), _ptr(lidx), _ptr(scale),
                                           _ptr(idx), n_groups, G, larr, n_levels, garr, n_grid,
                                           dtype_code(w), _stream())
@@ -266,8 +285,8 @@ def awq_layer(W: torch.Tensor, feats: torch.Tensor, n_bit: int, group: int, n_pr
     assert feats.shape[1] == K
     out = torch.empty_like(W)
     mask = torch.empty(K, dtype=torch.uint8, device=W.device) if return_mask else None
-    with torch.cuda.device(W.device):
-        work = _work(W.device, 2 * K)
+    with _on(W.device):
+        work = _work(W.device, 3 * K)
         rc = _lib.load().b200q_awq_layer(W.data_ptr(), out.data_ptr(), N, K, group, n_bit,
                                          feats.data_ptr(), feats.shape[0], dtype_code(feats),
                                          n_protect, float(scale_factor), work.data_ptr(), _ptr(mask),
@@ -281,8 +300,8 @@ def gptq_parity_layer(W: torch.Tensor, n_bit: int) -> torch.Tensor:
     W = W.contiguous()
     N, K = W.shape
     out = torch.empty_like(W)
-    with torch.cuda.device(W.device):
-        work = _work(W.device, K)
+    with _on(W.device):
+        work = _work(W.device, 2 * K)
         rc = _lib.load().b200q_gptq_parity_layer(W.data_ptr(), out.data_ptr(), N, K, n_bit,
                                                  work.data_ptr(), dtype_code(W), _stream())
     _lib.check(rc, "gptq_parity_layer")
@@ -300,8 +319,8 @@ def smoothquant_layer(W: torch.Tensor, act_scale: torch.Tensor, alpha: float, n_
     assert a.numel() == K, "act_scales length does not match in_features"
     out = torch.empty_like(W)
     s = torch.empty(K, dtype=torch.float32, device=W.device)
-    with torch.cuda.device(W.device):
-        work = _work(W.device, K)
+    with _on(W.device):
+        work = _work(W.device, 2 * K)
         rc = _lib.load().b200q_smoothquant_layer(W.data_ptr(), out.data_ptr(), N, K, group, n_bit,
                                                  a.data_ptr(), float(alpha),
                                                  DTYPE_CODE.get(act_scale.dtype, 0), s.data_ptr(),

@@ -38,8 +38,7 @@ def run_layers(items: Sequence[Tuple[str, nn.Linear]], compute: Compute) -> None
         return
     if all(m.weight.is_cuda for _, m in items):
         for name, m in items:
-            with torch.cuda.device(m.weight.device):
-                out = compute(name, m, m.weight.data.contiguous())
+            out = compute(name, m, m.weight.data)
             if out is not None:
                 _assign(m, out)
         return

@@ -175,6 +175,59 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) {
   return fminf(fmaxf(x, lo), hi);
 }
 
+// ---- exact division by a reused divisor ---------------------------------------------------------
+// a / b correctly rounded (bit-identical to IEEE / torch's CPU division) when the same b divides
+// many values: y = RN(1/b) once, then q0 = a*y and two Markstein corrections
+//     r = fma(-b, q, a);  q = fma(r, y, q)
+// The first makes q faithful, the second (Markstein's theorem: y correctly rounded, q faithful, r
+// exact) makes it the correctly rounded quotient — 5 FP32-pipe ops against the ~15-instruction
+// __fdiv_rn sequence, which is what moves the fake-quant kernels from issue-bound to HBM-bound.
+// Operands outside [1e-18, 1e18] (where r could underflow) take __fdiv_rn.  b200q_selftest_div
+// checks the identity against __fdiv_rn on the GPU.
+struct Divisor {
+  float b, y;
+  bool fast;
+  __device__ __forceinline__ Divisor() : b(1.f), y(1.f), fast(true) {}
+  __device__ __forceinline__ explicit Divisor(float b_) {
+    b = b_;
+    y = __frcp_rn(b_);
+    const float ab = fabsf(b_);
+    fast = ab > 1e-18f && ab < 1e18f;
+  }
+  __device__ __forceinline__ Divisor(float b_, float y_) : b(b_), y(y_) {
+    const float ab = fabsf(b_);
+    fast = ab > 1e-18f && ab < 1e18f;
+  }
+  // the unguarded core: exact for |a| and |b| in [1e-18, 1e18]; for smaller |a| the quotient may
+  // be 1-2 ulp off (fine where it is rounded to an integer code and |a / b| < 1/4 anyway)
+  __device__ __forceinline__ float div_core(float a) const {
+    float q = a * y;
+    float r = fmaf(-b, q, a);
+    q = fmaf(r, y, q);
+    r = fmaf(-b, q, a);
+    return fmaf(r, y, q);
+  }
+  __device__ __forceinline__ float div(float a) const {
+    const float aa = fabsf(a);
+    if (fast && ((aa > 1e-18f && aa < 1e18f) || aa == 0.f)) {
+      float q = a * y;
+      float r = fmaf(-b, q, a);
+      q = fmaf(r, y, q);
+      r = fmaf(-b, q, a);
+      return fmaf(r, y, q);
+    }
+    return __fdiv_rn(a, b);
+  }
+};
+
+// round-half-to-even on the FP32 pipe (rintf is a quarter-rate XU-pipe conversion): two FADDs.
+// Exact for |x| < 2^22.  Larger |x| come back within 2 of x, i.e. still far beyond any code range
+// (<= 2^16), so this is ONLY for values that are clamped to the code range right after.
+__device__ __forceinline__ float rint_then_clamped(float x) {
+  const float magic = 12582912.f;  // 1.5 * 2^23
+  return (x + magic) - magic;
+}
+
 // dtype dispatch on the host
 #define B200Q_DISPATCH_DTYPE(dtype, T, ...)                            \
   switch (dtype) {                                                     \

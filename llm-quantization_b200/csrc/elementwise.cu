@@ -141,6 +141,9 @@ gptq_parity_kernel(const T* __restrict__ W, T* __restrict__ out, int8_t* __restr
     for (int j = 0; j < VEC; ++j) scales[col0 + j] = s[j];
   }
   const float lo = -maxint - 1.f, hi = maxint;
+  Divisor d[VEC];                       // the column scale divides every row: y = 1/s once
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) d[j] = Divisor(s[j]);
   if constexpr (VECTOR) {
     int64_t r = r0 + ty;
     for (; r + 24 < r1; r += 32) {
@@ -153,7 +156,7 @@ gptq_parity_kernel(const T* __restrict__ W, T* __restrict__ out, int8_t* __restr
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           // clamp(round(w / scale), -max_int-1, max_int) * scale    gptq_quantizer.py:187-188
-          q[j] = clampf(rintf(ST<T>::rnd(__fdiv_rn(a[u][j], s[j]))), lo, hi);
+          q[j] = clampf(rint_then_clamped(ST<T>::rnd(d[j].div(a[u][j]))), lo, hi);
           a[u][j] = ST<T>::rnd(q[j] * s[j]);
         }
         store_vec<T>(out + (r + 8 * u) * K + col0, a[u]);
@@ -169,7 +172,7 @@ gptq_parity_kernel(const T* __restrict__ W, T* __restrict__ out, int8_t* __restr
       load_vec<T>(W + r * ld + col0, a);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        q[j] = clampf(rintf(ST<T>::rnd(__fdiv_rn(a[j], s[j]))), lo, hi);
+        q[j] = clampf(rint_then_clamped(ST<T>::rnd(d[j].div(a[j]))), lo, hi);
         a[j] = ST<T>::rnd(q[j] * s[j]);
       }
       store_vec<T>(out + r * K + col0, a);
@@ -182,7 +185,7 @@ gptq_parity_kernel(const T* __restrict__ W, T* __restrict__ out, int8_t* __restr
   } else {
     for (int64_t r = r0 + ty; r < r1; r += 8) {
       const float w = to_f(W[r * ld + col0]);
-      const float q = clampf(rintf(ST<T>::rnd(__fdiv_rn(w, s[0]))), lo, hi);
+      const float q = clampf(rint_then_clamped(ST<T>::rnd(d[0].div(w))), lo, hi);
       out[r * K + col0] = from_f<T>(q * s[0]);
       if (codes != nullptr) codes[r * K + col0] = (int8_t)q;
     }
@@ -199,20 +202,23 @@ struct GroupQuantArgs {
   int64_t G;   // elements per group
   int64_t K;   // row length (for column ops)
   const float* colvec;
+  const float* colrcp;   // RN(1 / colvec[k]) when the caller has it (else computed per element)
+  int binary;            // colvec holds only {1, bin_factor}: reciprocal = select(1, bin_rcp)
+  float bin_rcp;
   void* codes;
   float* scales;
   float* zeros;
 };
 
 template <typename T, int COLOP>
-__device__ __forceinline__ float pre_op(float w, float cv) {
-  if constexpr (COLOP == B200Q_COLOP_MUL_DIV) return ST<T>::rnd(w * cv);  // awq_quantizer.py:70
-  if constexpr (COLOP == B200Q_COLOP_DIV) return ST<T>::rnd(__fdiv_rn(w, cv));  // smooth:170
+__device__ __forceinline__ float pre_op(float w, const Divisor& cv) {
+  if constexpr (COLOP == B200Q_COLOP_MUL_DIV) return ST<T>::rnd(w * cv.b);  // awq_quantizer.py:70
+  if constexpr (COLOP == B200Q_COLOP_DIV) return ST<T>::rnd(cv.div(w));     // smooth:170
   return w;
 }
 template <typename T, int COLOP>
-__device__ __forceinline__ float post_op(float o, float cv) {
-  if constexpr (COLOP == B200Q_COLOP_MUL_DIV) return ST<T>::rnd(__fdiv_rn(o, cv));  // awq:81
+__device__ __forceinline__ float post_op(float o, const Divisor& cv) {
+  if constexpr (COLOP == B200Q_COLOP_MUL_DIV) return ST<T>::rnd(cv.div(o));  // awq:81
   return o;
 }
 
@@ -228,102 +234,205 @@ __device__ __forceinline__ void group_params(float mx, float mn, float maxint, f
     // scales = (max - min).clamp(min=1e-5) / max_int               quantization_utils.py:395
     scale = ST<T>::rnd(__fdiv_rn(fmaxf(ST<T>::rnd(mx - mn), clamp_min_1e5<T>()), maxint));
     // zeros = (-round(min / scales)).clamp_(0, max_int)            quantization_utils.py:396
-    zp = clampf(-rintf(ST<T>::rnd(__fdiv_rn(mn, scale))), 0.f, maxint);
+    zp = clampf(-rint_then_clamped(ST<T>::rnd(__fdiv_rn(mn, scale))), 0.f, maxint);
   }
 }
 template <typename T, bool SYM>
-__device__ __forceinline__ float quant_one(float x, float scale, float zp, float maxint,
+__device__ __forceinline__ float quant_one(float x, const Divisor& scale, float zp, float maxint,
                                            float& code) {
   if constexpr (SYM) {
-    code = clampf(rintf(ST<T>::rnd(__fdiv_rn(x, scale))), -maxint - 1.f, maxint);
-    return ST<T>::rnd(code * scale);
+    code = clampf(rint_then_clamped(ST<T>::rnd(scale.div(x))), -maxint - 1.f, maxint);
+    return ST<T>::rnd(code * scale.b);
   } else {
     // w_q = clamp(round(w / scales) + zeros, 0, max_int); w = (w_q - zeros) * scales   :402-405
-    code = clampf(ST<T>::rnd(rintf(ST<T>::rnd(__fdiv_rn(x, scale))) + zp), 0.f, maxint);
-    return ST<T>::rnd(ST<T>::rnd(code - zp) * scale);
+    code = clampf(ST<T>::rnd(rint_then_clamped(ST<T>::rnd(scale.div(x))) + zp), 0.f, maxint);
+    return ST<T>::rnd(ST<T>::rnd(code - zp) * scale.b);
   }
 }
 
-// G == 128: a group is one 128-bit access per lane across 32 (fp32) or 16 (16-bit) lanes.
+// G == 128: EIGHT lanes own one group, 16 elements per lane as 4 (fp32) or 2 (16-bit) 128-bit
+// accesses; a warp works on four consecutive groups.  Compared with one-warp-per-group this cuts
+// the per-group scalar work (min/max shuffles, scale / zero-point divisions, reciprocal) that
+// every lane repeats from 1/4 to 1/16 of an element's cost, and the per-element division is the
+// 5-op reused-divisor form — together ~20 thread-instructions per element, below the ~44 the SMs
+// can issue per element at HBM speed.  Groups whose values leave [1e-18, 1e18] (where the
+// unguarded division core is not proven exact) are redone with plain IEEE divisions.
+template <typename T, bool SYM, int COLOP, bool EXACT_SLOW>
+__device__ __forceinline__ void quantize_group16(float (&x)[16], const float (&cv)[16],
+                                                 const float (&cr)[16], float mx, float mn,
+                                                 const GroupQuantArgs& a, float& scale, float& zp,
+                                                 float (&code)[16]) {
+  group_params<T, SYM>(mx, mn, a.maxint, scale, zp);
+  const Divisor sd(scale);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    float q;
+    if constexpr (EXACT_SLOW) q = __fdiv_rn(x[e], scale);
+    else q = sd.div_core(x[e]);
+    float o;
+    if constexpr (SYM) {
+      code[e] = clampf(rint_then_clamped(ST<T>::rnd(q)), -a.maxint - 1.f, a.maxint);
+      o = ST<T>::rnd(code[e] * scale);
+    } else {
+      code[e] = clampf(ST<T>::rnd(rint_then_clamped(ST<T>::rnd(q)) + zp), 0.f, a.maxint);
+      o = ST<T>::rnd(ST<T>::rnd(code[e] - zp) * scale);
+    }
+    if constexpr (COLOP == B200Q_COLOP_MUL_DIV) {
+      if constexpr (EXACT_SLOW) o = ST<T>::rnd(__fdiv_rn(o, cv[e]));
+      else o = ST<T>::rnd(Divisor(cv[e], cr[e]).div_core(o));
+    }
+    x[e] = o;
+  }
+}
+
 template <typename T, bool SYM, int COLOP>
 __global__ void __launch_bounds__(256)
 group128_kernel(const T* __restrict__ W, T* __restrict__ out, GroupQuantArgs a) {
-  constexpr int VEC = ST<T>::VEC;
-  constexpr int LPG = 128 / VEC;   // lanes per group
-  constexpr int GPW = 32 / LPG;    // groups per warp per slot
-  constexpr int ILP = 4;
+  constexpr int VEC = ST<T>::VEC;   // elements per 128-bit access
+  constexpr int NV = 16 / VEC;      // accesses per lane
   const int lane = threadIdx.x & 31;
-  const int sub = lane / LPG, lig = lane % LPG;
+  const int l8 = lane & 7, sub = lane >> 3;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t groups_per_row = a.K / 128;
-  for (int64_t base = warp * (GPW * ILP); base < a.n_groups; base += nwarps * (GPW * ILP)) {
-    float v[ILP][VEC];
-    float cv[ILP][VEC];
-    int64_t g[ILP];
+  for (int64_t base = warp * 4; base < a.n_groups; base += nwarps * 4) {
+    const int64_t g = base + sub;
+    const bool valid = g < a.n_groups;
+    const int64_t gg = valid ? g : a.n_groups - 1;
+    const T* wp = W + gg * 128 + l8 * VEC;
+    float x[16], cv[16], cr[16];
 #pragma unroll
-    for (int u = 0; u < ILP; ++u) {
-      g[u] = base + u * GPW + sub;
-      if (g[u] < a.n_groups) {
-        load_vec<T>(W + g[u] * 128 + lig * VEC, v[u]);
-        if constexpr (COLOP != B200Q_COLOP_NONE) {
-          const float* c = a.colvec + (g[u] % groups_per_row) * 128 + lig * VEC;
+    for (int i = 0; i < NV; ++i) {
+      float t[VEC];
+      load_vec<T>(wp + i * 8 * VEC, t);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) x[i * VEC + j] = t[j];
+    }
+    if constexpr (COLOP != B200Q_COLOP_NONE) {
+      const int64_t c0 = (gg % groups_per_row) * 128 + l8 * VEC;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < VEC; j += 4) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(a.colvec + c0 + i * 8 * VEC + j));
+          cv[i * VEC + j] = f.x; cv[i * VEC + j + 1] = f.y;
+          cv[i * VEC + j + 2] = f.z; cv[i * VEC + j + 3] = f.w;
+        }
+      if (a.binary) {
+        // colvec is {1, factor}: the reciprocal is a select, not a second vector
+#pragma unroll
+        for (int e = 0; e < 16; ++e) cr[e] = (cv[e] == 1.f) ? 1.f : a.bin_rcp;
+      } else if (a.colrcp != nullptr) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
 #pragma unroll
           for (int j = 0; j < VEC; j += 4) {
-            const float4 f = __ldg(reinterpret_cast<const float4*>(c + j));
-            cv[u][j] = f.x; cv[u][j + 1] = f.y; cv[u][j + 2] = f.z; cv[u][j + 3] = f.w;
+            const float4 f = __ldg(reinterpret_cast<const float4*>(a.colrcp + c0 + i * 8 * VEC + j));
+            cr[i * VEC + j] = f.x; cr[i * VEC + j + 1] = f.y;
+            cr[i * VEC + j + 2] = f.z; cr[i * VEC + j + 3] = f.w;
           }
-        }
       } else {
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) { v[u][j] = 0.f; cv[u][j] = 1.f; }
+        for (int e = 0; e < 16; ++e) cr[e] = __frcp_rn(cv[e]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) { cv[e] = 1.f; cr[e] = 1.f; }
+    }
+    // column pre-op.  The unguarded division core is exact for operands in [1e-18, 1e18]; results
+    // outside that (or NaN) send the whole group through the IEEE path below.
+    bool cfast = true;
+    if constexpr (COLOP == B200Q_COLOP_MUL_DIV) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        x[e] = ST<T>::rnd(x[e] * cv[e]);                                   // awq_quantizer.py:70
+        cfast = cfast && (fabsf(cv[e]) > 1e-18f) && (fabsf(cv[e]) < 1e18f);
+      }
+    } else if constexpr (COLOP == B200Q_COLOP_DIV) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        cfast = cfast && (fabsf(cv[e]) > 1e-18f) && (fabsf(cv[e]) < 1e18f);
+        x[e] = ST<T>::rnd(Divisor(cv[e], cr[e]).div_core(x[e]));          // smooth_quant:170
       }
     }
+    float mx, mn;
+    if constexpr (SYM) {
+      mx = fabsf(x[0]);
 #pragma unroll
-    for (int u = 0; u < ILP; ++u) {
-      float mx, mn;
+      for (int e = 1; e < 16; ++e) mx = fmaxf(mx, fabsf(x[e]));
+      mn = 0.f;
+    } else {
+      mx = x[0]; mn = x[0];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) v[u][j] = pre_op<T, COLOP>(v[u][j], cv[u][j]);
+      for (int e = 1; e < 16; ++e) { mx = fmaxf(mx, x[e]); mn = fminf(mn, x[e]); }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if constexpr (!SYM) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    const float gmax = fmaxf(fabsf(mx), fabsf(mn));
+    // group-uniform decision (all 8 lanes see the same gmax; cfast is combined across them)
+    unsigned ok = __ballot_sync(0xffffffffu, cfast);
+    const bool fast = (((ok >> (sub * 8)) & 0xffu) == 0xffu) && (gmax < 1e18f);
+    float scale, zp, code[16];
+    if (fast) {
+      quantize_group16<T, SYM, COLOP, false>(x, cv, cr, mx, mn, a, scale, zp, code);
+    } else {
+      // rare: reload and redo everything with IEEE divisions
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float t[VEC];
+        load_vec<T>(wp + i * 8 * VEC, t);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) x[i * VEC + j] = t[j];
+      }
+      if constexpr (COLOP == B200Q_COLOP_MUL_DIV) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) x[e] = ST<T>::rnd(x[e] * cv[e]);
+      } else if constexpr (COLOP == B200Q_COLOP_DIV) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) x[e] = ST<T>::rnd(__fdiv_rn(x[e], cv[e]));
+      }
       if constexpr (SYM) {
-        mx = fabsf(v[u][0]);
+        mx = fabsf(x[0]);
 #pragma unroll
-        for (int j = 1; j < VEC; ++j) mx = fmaxf(mx, fabsf(v[u][j]));
-        mn = 0.f;
+        for (int e = 1; e < 16; ++e) mx = fmaxf(mx, fabsf(x[e]));
       } else {
-        mx = v[u][0]; mn = v[u][0];
+        mx = x[0]; mn = x[0];
 #pragma unroll
-        for (int j = 1; j < VEC; ++j) { mx = fmaxf(mx, v[u][j]); mn = fminf(mn, v[u][j]); }
+        for (int e = 1; e < 16; ++e) { mx = fmaxf(mx, x[e]); mn = fminf(mn, x[e]); }
       }
+      // this branch is taken by whole 8-lane teams, so a width-8 shuffle is well defined
 #pragma unroll
-      for (int o = LPG / 2; o > 0; o >>= 1) {
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if constexpr (!SYM) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      for (int o = 4; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(__activemask(), mx, o, 8));
+        if constexpr (!SYM) mn = fminf(mn, __shfl_xor_sync(__activemask(), mn, o, 8));
       }
-      float scale, zp;
-      group_params<T, SYM>(mx, mn, a.maxint, scale, zp);
-      float code[VEC];
+      quantize_group16<T, SYM, COLOP, true>(x, cv, cr, mx, mn, a, scale, zp, code);
+    }
+    if (valid) {
+      T* op = out + g * 128 + l8 * VEC;
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        const float o = quant_one<T, SYM>(v[u][j], scale, zp, a.maxint, code[j]);
-        v[u][j] = post_op<T, COLOP>(o, cv[u][j]);
+      for (int i = 0; i < NV; ++i) {
+        float t[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) t[j] = x[i * VEC + j];
+        store_vec<T>(op + i * 8 * VEC, t);
       }
-      if (g[u] < a.n_groups) {
-        store_vec<T>(out + g[u] * 128 + lig * VEC, v[u]);
-        if (a.codes != nullptr) {
-          if constexpr (SYM) {
-            int8_t* c = static_cast<int8_t*>(a.codes) + g[u] * 128 + lig * VEC;
+      if (a.codes != nullptr) {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) c[j] = (int8_t)code[j];
-          } else {
-            uint8_t* c = static_cast<uint8_t*>(a.codes) + g[u] * 128 + lig * VEC;
+        for (int i = 0; i < NV; ++i)
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) c[j] = (uint8_t)code[j];
+          for (int j = 0; j < VEC; ++j) {
+            const int64_t at = g * 128 + i * 8 * VEC + l8 * VEC + j;
+            if constexpr (SYM) static_cast<int8_t*>(a.codes)[at] = (int8_t)code[i * VEC + j];
+            else static_cast<uint8_t*>(a.codes)[at] = (uint8_t)code[i * VEC + j];
           }
-        }
-        if (lig == 0) {
-          if (a.scales != nullptr) a.scales[g[u]] = scale;
-          if (a.zeros != nullptr) a.zeros[g[u]] = zp;
-        }
+      }
+      if (l8 == 0) {
+        if (a.scales != nullptr) a.scales[g] = scale;
+        if (a.zeros != nullptr) a.zeros[g] = zp;
       }
     }
   }
@@ -340,8 +449,8 @@ group_generic_kernel(const T* __restrict__ W, T* __restrict__ out, GroupQuantArg
     const int64_t off = g * a.G;
     float mx = SYM ? 0.f : -INFINITY, mn = INFINITY;
     for (int64_t i = lane; i < a.G; i += 32) {
-      float cv = 1.f;
-      if constexpr (COLOP != B200Q_COLOP_NONE) cv = a.colvec[(off + i) % a.K];
+      Divisor cv;
+      if constexpr (COLOP != B200Q_COLOP_NONE) cv = Divisor(a.colvec[(off + i) % a.K]);
       const float x = pre_op<T, COLOP>(to_f(W[off + i]), cv);
       if constexpr (SYM) mx = fmaxf(mx, fabsf(x));
       else { mx = fmaxf(mx, x); mn = fminf(mn, x); }
@@ -353,12 +462,13 @@ group_generic_kernel(const T* __restrict__ W, T* __restrict__ out, GroupQuantArg
     }
     float scale, zp;
     group_params<T, SYM>(mx, mn, a.maxint, scale, zp);
+    const Divisor sd(scale);
     for (int64_t i = lane; i < a.G; i += 32) {
-      float cv = 1.f;
-      if constexpr (COLOP != B200Q_COLOP_NONE) cv = a.colvec[(off + i) % a.K];
+      Divisor cv;
+      if constexpr (COLOP != B200Q_COLOP_NONE) cv = Divisor(a.colvec[(off + i) % a.K]);
       const float x = pre_op<T, COLOP>(to_f(W[off + i]), cv);
       float code;
-      const float o = post_op<T, COLOP>(quant_one<T, SYM>(x, scale, zp, a.maxint, code), cv);
+      const float o = post_op<T, COLOP>(quant_one<T, SYM>(x, sd, zp, a.maxint, code), cv);
       out[off + i] = from_f<T>(o);
       if (a.codes != nullptr) {
         if constexpr (SYM) static_cast<int8_t*>(a.codes)[off + i] = (int8_t)code;
@@ -377,8 +487,7 @@ static int launch_group_quant(const void* W, void* out, const GroupQuantArgs& a,
                               cudaStream_t st) {
   if (a.n_groups == 0) return B200Q_OK;
   if (fast128) {
-    constexpr int GPW = 32 / (128 / ST<T>::VEC);
-    const int64_t warps_needed = (a.n_groups + GPW * 4 - 1) / (GPW * 4);
+    const int64_t warps_needed = (a.n_groups + 3) / 4;
     int64_t blocks = (warps_needed + 7) / 8;
     blocks = std::min<int64_t>(blocks, (int64_t)kNumSMs * 8 * 4);  // grid-stride beyond 4 waves
     if (blocks > kNumSMs) blocks = blocks / kNumSMs * kNumSMs;      // whole waves
@@ -412,8 +521,9 @@ __device__ __forceinline__ float torch_pow_scalar(float x, float e) {
 }
 
 __global__ void smooth_scale_kernel(const float* __restrict__ act, const float* __restrict__ wmax,
-                                    float* __restrict__ s, int64_t K, float alpha, float one_m_alpha,
-                                    int act_dtype, int w_dtype, int res_dtype) {
+                                    float* __restrict__ s, float* __restrict__ s_rcp, int64_t K,
+                                    float alpha, float one_m_alpha, int act_dtype, int w_dtype,
+                                    int res_dtype) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   // act_scale = clamp(act_scale, 1e-5); weight_scale = clamp(weight_scale, 1e-5)   smooth:159-160
@@ -422,7 +532,9 @@ __global__ void smooth_scale_kernel(const float* __restrict__ act, const float* 
   // s = pow(a, alpha) / pow(w, 1 - alpha); s = clamp(s, 1e-5)                       smooth:165-166
   const float pa = rnd_rt(torch_pow_scalar(a, alpha), act_dtype);
   const float pw = rnd_rt(torch_pow_scalar(w, one_m_alpha), w_dtype);
-  s[k] = fmaxf(rnd_rt(__fdiv_rn(pa, pw), res_dtype), rnd_rt(1e-5f, res_dtype));
+  const float sk = fmaxf(rnd_rt(__fdiv_rn(pa, pw), res_dtype), rnd_rt(1e-5f, res_dtype));
+  s[k] = sk;
+  if (s_rcp != nullptr) s_rcp[k] = __frcp_rn(sk);
 }
 
 template <typename T, bool MUL, bool VECTOR>
@@ -436,8 +548,9 @@ col_scale_kernel(const T* __restrict__ W, T* __restrict__ out, const float* __re
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = min(N, r0 + (int64_t)rows_per_block);
   float sv[VEC];
+  Divisor sd[VEC];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) sv[j] = s[col0 + j];
+  for (int j = 0; j < VEC; ++j) { sv[j] = s[col0 + j]; sd[j] = Divisor(sv[j]); }
   if constexpr (VECTOR) {
     int64_t r = r0 + ty;
     for (; r + 24 < r1; r += 32) {
@@ -448,7 +561,7 @@ col_scale_kernel(const T* __restrict__ W, T* __restrict__ out, const float* __re
       for (int u = 0; u < 4; ++u) {
 #pragma unroll
         for (int j = 0; j < VEC; ++j)
-          a[u][j] = ST<T>::rnd(MUL ? a[u][j] * sv[j] : __fdiv_rn(a[u][j], sv[j]));
+          a[u][j] = ST<T>::rnd(MUL ? a[u][j] * sv[j] : sd[j].div(a[u][j]));
         store_vec<T>(out + (r + 8 * u) * K + col0, a[u]);
       }
     }
@@ -456,13 +569,13 @@ col_scale_kernel(const T* __restrict__ W, T* __restrict__ out, const float* __re
       float a[ST<T>::VEC];
       load_vec<T>(W + r * K + col0, a);
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) a[j] = ST<T>::rnd(MUL ? a[j] * sv[j] : __fdiv_rn(a[j], sv[j]));
+      for (int j = 0; j < VEC; ++j) a[j] = ST<T>::rnd(MUL ? a[j] * sv[j] : sd[j].div(a[j]));
       store_vec<T>(out + r * K + col0, a);
     }
   } else {
     for (int64_t r = r0 + ty; r < r1; r += 8) {
       const float w = to_f(W[r * K + col0]);
-      out[r * K + col0] = from_f<T>(MUL ? w * sv[0] : __fdiv_rn(w, sv[0]));
+      out[r * K + col0] = from_f<T>(MUL ? w * sv[0] : sd[0].div(w));
     }
   }
 }
@@ -551,8 +664,9 @@ __device__ __forceinline__ uint32_t ordered_bits(float x) {
 }
 
 __global__ void __launch_bounds__(1024)
-topk_colmul_kernel(const float* __restrict__ v, int K, int k, float factor,
-                   float* __restrict__ colmul, uint8_t* __restrict__ mask) {
+topk_colmul_kernel(const float* __restrict__ v, int K, int k, float factor, float factor_rcp,
+                   float* __restrict__ colmul, float* __restrict__ colrcp,
+                   uint8_t* __restrict__ mask) {
   __shared__ unsigned int hist[256];
   __shared__ unsigned int s_prefix, s_need, s_eq_base[1024];
   const int tid = threadIdx.x;
@@ -601,6 +715,7 @@ topk_colmul_kernel(const float* __restrict__ v, int K, int k, float factor,
     bool take = u > thr;
     if (u == thr) { take = seen < need_eq; ++seen; }
     colmul[i] = take ? factor : 1.f;
+    if (colrcp != nullptr) colrcp[i] = take ? factor_rcp : 1.f;
     if (mask != nullptr) mask[i] = take ? 1 : 0;
   }
 }
@@ -659,9 +774,10 @@ int b200q_gptq_parity_quant(const void* W, void* out, int8_t* codes, const float
   return check_launch("gptq_parity_quant");
 }
 
-int b200q_group_fakequant(const void* W, void* out, void* codes, float* scales, float* zeros,
-                          int64_t N, int64_t K, int64_t group, int n_bit, int symmetric, int colop,
-                          const float* colvec, int dtype, void* stream) {
+static int group_fakequant_impl(const void* W, void* out, void* codes, float* scales, float* zeros,
+                               int64_t N, int64_t K, int64_t group, int n_bit, int symmetric,
+                               int colop, const float* colvec, const float* colrcp,
+                               float binary_rcp, int dtype, void* stream) {
   B200Q_REQUIRE(W && out, "group_fakequant: null pointer");
   B200Q_REQUIRE(N >= 0 && K > 0, "group_fakequant: bad shape");
   B200Q_REQUIRE(n_bit >= 1 && n_bit <= 16, "group_fakequant: n_bit must be in [1,16]");
@@ -680,11 +796,15 @@ int b200q_group_fakequant(const void* W, void* out, void* codes, float* scales, 
   a.G = G;
   a.K = K;
   a.colvec = colvec;
+  a.colrcp = colrcp;
+  a.binary = binary_rcp != 0.f;      // colvec is {1, factor}; binary_rcp = RN(1 / factor)
+  a.bin_rcp = binary_rcp;
   a.codes = codes;
   a.scales = scales;
   a.zeros = zeros;
   const bool fast = (G == 128) && aligned16(W) && aligned16(out) &&
-                    (colop == B200Q_COLOP_NONE || aligned16(colvec));
+                    (colop == B200Q_COLOP_NONE ||
+                     (aligned16(colvec) && (colrcp == nullptr || aligned16(colrcp))));
   KernelScope scope("group_fakequant", 2.0 * N * K * elem_size(dtype), 0, st);
 #define B200Q_GQ(SYM, OP) return launch_group_quant<T, SYM, OP>(W, out, a, fast, st)
   B200Q_DISPATCH_DTYPE(dtype, T, {
@@ -702,6 +822,13 @@ int b200q_group_fakequant(const void* W, void* out, void* codes, float* scales, 
   return B200Q_OK;
 }
 
+int b200q_group_fakequant(const void* W, void* out, void* codes, float* scales, float* zeros,
+                          int64_t N, int64_t K, int64_t group, int n_bit, int symmetric, int colop,
+                          const float* colvec, int dtype, void* stream) {
+  return group_fakequant_impl(W, out, codes, scales, zeros, N, K, group, n_bit, symmetric, colop,
+                              colvec, nullptr, 0.f, dtype, stream);
+}
+
 static int promote_dtype(int a, int b) {
   if (a == b) return a;
   return B200Q_F32;
@@ -714,7 +841,7 @@ int b200q_smooth_scale(const float* act_scale, const float* wmax, float* s, int6
   // the reference evaluates 1.0 - alpha in Python doubles before torch narrows it
   const float one_m_alpha = (float)(1.0 - (double)alpha);
   smooth_scale_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(
-      act_scale, wmax, s, K, alpha, one_m_alpha, act_dtype, w_dtype,
+      act_scale, wmax, s, nullptr, K, alpha, one_m_alpha, act_dtype, w_dtype,
       promote_dtype(act_dtype, w_dtype));
   count_launch();
   return check_launch("smooth_scale");
@@ -795,7 +922,8 @@ int b200q_topk_colmul(const float* importance, int64_t K, int64_t k, float facto
   B200Q_REQUIRE(importance && colmul && K > 0 && k >= 0 && k <= K && K < (1ll << 30),
                 "topk_colmul: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  topk_colmul_kernel<<<1, 1024, 0, st>>>(importance, (int)K, (int)k, factor, colmul, mask);
+  topk_colmul_kernel<<<1, 1024, 0, st>>>(importance, (int)K, (int)k, factor, 1.0f / factor, colmul,
+                                         nullptr, mask);
   count_launch();
   return check_launch("topk_colmul");
 }
@@ -806,14 +934,21 @@ int b200q_awq_layer(const void* W, void* out, int64_t N, int64_t K, int64_t grou
                     float scale_factor, float* work, uint8_t* salient_mask, int dtype,
                     void* stream) {
   B200Q_REQUIRE(feats && work && n_feats > 0, "awq_layer: bad argument");
-  float* importance = work;      // [K]
-  float* colmul = work + K;      // [K]
+  B200Q_REQUIRE(K > 0 && n_protect >= 0 && n_protect <= K && K < (1ll << 30), "awq_layer: bad K");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* importance = work;          // [K]
+  float* colmul = work + K;          // [K]   scale_factor on the salient columns, 1 elsewhere
+  float* colrcp = work + 2 * K;      // [K]   RN(1 / colmul)
   int rc = b200q_seq_sum_rows(feats, n_feats, K, feat_dtype, importance, stream);
   if (rc != B200Q_OK) return rc;
-  rc = b200q_topk_colmul(importance, K, n_protect, scale_factor, colmul, salient_mask, stream);
+  topk_colmul_kernel<<<1, 1024, 0, st>>>(importance, (int)K, (int)n_protect, scale_factor,
+                                         1.0f / scale_factor, colmul, colrcp, salient_mask);
+  count_launch();
+  rc = check_launch("awq_layer/topk");
   if (rc != B200Q_OK) return rc;
-  return b200q_group_fakequant(W, out, nullptr, nullptr, nullptr, N, K, group, n_bit, 0,
-                               B200Q_COLOP_MUL_DIV, colmul, dtype, stream);
+  return group_fakequant_impl(W, out, nullptr, nullptr, nullptr, N, K, group, n_bit, 0,
+                              B200Q_COLOP_MUL_DIV, colmul, colrcp, 1.0f / scale_factor, dtype,
+                              stream);
 }
 
 int b200q_gptq_parity_layer(const void* W, void* out, int64_t N, int64_t K, int n_bit,
@@ -826,13 +961,92 @@ int b200q_gptq_parity_layer(const void* W, void* out, int64_t N, int64_t K, int 
 int b200q_smoothquant_layer(const void* W, void* out, int64_t N, int64_t K, int64_t group,
                             int n_bit, const float* act_scale, float alpha, int act_dtype,
                             float* s, float* work, int dtype, void* stream) {
-  B200Q_REQUIRE(act_scale && s && work, "smoothquant_layer: bad argument");
-  int rc = b200q_col_absmax(W, N, K, K, dtype, work, 0, stream);
+  B200Q_REQUIRE(act_scale && s && work && K > 0, "smoothquant_layer: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* colmax = work;              // [K]
+  float* s_rcp = work + K;           // [K]   RN(1 / s)
+  int rc = b200q_col_absmax(W, N, K, K, dtype, colmax, 0, stream);
   if (rc != B200Q_OK) return rc;
-  rc = b200q_smooth_scale(act_scale, work, s, K, alpha, act_dtype, dtype, stream);
+  smooth_scale_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(
+      act_scale, colmax, s, s_rcp, K, alpha, (float)(1.0 - (double)alpha), act_dtype, dtype,
+      promote_dtype(act_dtype, dtype));
+  count_launch();
+  rc = check_launch("smoothquant_layer/scale");
   if (rc != B200Q_OK) return rc;
-  return b200q_group_fakequant(W, out, nullptr, nullptr, nullptr, N, K, group, n_bit, 0,
-                               B200Q_COLOP_DIV, s, dtype, stream);
+  return group_fakequant_impl(W, out, nullptr, nullptr, nullptr, N, K, group, n_bit, 0,
+                              B200Q_COLOP_DIV, s, s_rcp, 0.f, dtype, stream);
+}
+
+// ---- self test: Divisor::div against __fdiv_rn ------------------------------------------------
+}  // extern "C"
+
+namespace b200q {
+__global__ void selftest_div_kernel(uint64_t seed, int64_t n_per_thread, unsigned long long* bad,
+                                    float* first_a, float* first_b) {
+  uint64_t x = seed + 0x9E3779B97F4A7C15ull * (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x + 1);
+  auto next = [&]() {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    return x;
+  };
+  for (int64_t it = 0; it < n_per_thread; ++it) {
+    const uint64_t r = next();
+    // b: random mantissa, exponent in [-30, 30]; reused for 8 numerators like a group scale
+    const uint32_t bb = ((uint32_t)(r & 0x7fffff)) | ((uint32_t)(127 - 30 + (r >> 23) % 61) << 23);
+    const float b = __uint_as_float(bb);
+    const Divisor d(b);
+    for (int k = 0; k < 8; ++k) {
+      const uint64_t q = next();
+      float a;
+      if (k < 4) {
+        // random numerator, exponent in [-40, 40], random sign
+        const uint32_t ab = ((uint32_t)(q & 0x7fffff)) | ((uint32_t)(127 - 40 + (q >> 23) % 81) << 23) |
+                            ((uint32_t)(q >> 63) << 31);
+        a = __uint_as_float(ab);
+      } else {
+        // adversarial: a ~ b * (m + 0.5) +- a few ulps -> quotients next to rounding ties
+        const float m = (float)((q >> 8) % 64) + 0.5f;
+        a = __uint_as_float(__float_as_uint(b * m) + (int)(q & 7) - 3);
+      }
+      const float want = __fdiv_rn(a, b);
+      const float got = d.div(a);
+      if (__float_as_uint(want) != __float_as_uint(got)) {
+        if (atomicAdd(bad, 1ull) == 0) { *first_a = a; *first_b = b; }
+      }
+    }
+  }
+}
+}  // namespace b200q
+
+extern "C" {
+
+int b200q_selftest_div(int64_t n_quotients, uint64_t seed, int64_t* mismatches, void* stream) {
+  B200Q_REQUIRE(mismatches != nullptr && n_quotients > 0, "selftest_div: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long* d_bad = nullptr;
+  float* d_first = nullptr;
+  if (cudaMalloc(&d_bad, sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMalloc(&d_first, 2 * sizeof(float)) != cudaSuccess)
+    return fail(B200Q_ECUDA, "selftest_div: cudaMalloc");
+  cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), st);
+  const int blocks = kNumSMs * 8, threads = 256;
+  const int64_t per_thread = (n_quotients / 8 + (int64_t)blocks * threads - 1) / ((int64_t)blocks * threads);
+  b200q::selftest_div_kernel<<<blocks, threads, 0, st>>>(seed, per_thread, d_bad, d_first, d_first + 1);
+  count_launch();
+  unsigned long long h_bad = 0;
+  float h_first[2] = {0, 0};
+  cudaMemcpyAsync(&h_bad, d_bad, sizeof(h_bad), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(h_first, d_first, sizeof(h_first), cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(d_bad);
+  cudaFree(d_first);
+  if (e != cudaSuccess) return fail(B200Q_ECUDA, std::string("selftest_div: ") + cudaGetErrorString(e));
+  *mismatches = (int64_t)h_bad;
+  if (h_bad != 0) {
+    char buf[128];
+    snprintf(buf, sizeof(buf), "selftest_div: first mismatch a=%.9g b=%.9g", h_first[0], h_first[1]);
+    set_error(buf);
+  }
+  return B200Q_OK;
 }
 
 }  // extern "C"

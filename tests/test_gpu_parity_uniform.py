@@ -299,6 +299,17 @@ def test_topk_ties_take_lowest_indices():
     assert mask.cpu().nonzero().flatten().tolist() == [0, 1, 2, 100]
 
 
+def test_reused_divisor_division_is_ieee_exact():
+    """reciprocal + two Markstein corrections == __fdiv_rn on 2^31 random / adversarial pairs."""
+    import ctypes
+    from b200q import _lib
+    bad = ctypes.c_int64(-1)
+    rc = _lib.load().b200q_selftest_div(1 << 31, 12345, ctypes.byref(bad),
+                                        torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    assert bad.value == 0, _lib.load().b200q_last_error().decode()
+
+
 def test_profile_records_entry_points():
     from b200q import _lib, ops
     w = torch.randn(256, 1024, device="cuda")
