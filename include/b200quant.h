@@ -165,6 +165,21 @@ int b200q_apot_quant(const void* w, void* out, uint8_t* level_idx, float* best_s
                      const float* levels_host, int n_levels, const float* grid_host, int n_grid,
                      int dtype, void* stream);
 
+/* ---- GPTQ Hessian (tcgen05 tensor cores, TMA-fed) -------------------------------------------
+ * H (+)= sum_i a_i^2 * X_i^T X_i  with a_i = 1/(||X_i||_F + 1e-5); X is [n_samples *
+ * rows_per_sample, K] row-major and sample i is rows [i*rows_per_sample, (i+1)*rows_per_sample).
+ * ref: gptq_quantizer.py:137-144 (1-D features are samples of one row, :140-141).
+ * H is fp32 [K,K], fully written (both triangles); accumulate != 0 adds to its contents (ragged
+ * sample lists are fed as several calls).  norms_out (optional, fp32 [n_samples]) receives
+ * ||X_i||_F.  work: b200q_hessian_workspace(T, K, n_samples) bytes of device scratch.
+ * K must be a multiple of 8. */
+int64_t b200q_hessian_workspace(int64_t T, int64_t K, int n_samples);
+int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, int64_t K, int dtype,
+                        float* H, int accumulate, float* norms_out, void* work, void* stream);
+/* H = H * scale + damp * I     ref: gptq_quantizer.py:150 (scale = 1/len(input_feat), damp =
+ * perp_damp) and :160 (scale = 1, damp = 1e-6) */
+int b200q_hessian_finalize(float* H, int64_t K, float scale, float damp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             if verbose:
                 print(res.stderr)
     if force or _stale(LIB_PATH, objs):
-        cmd = [nvcc, *ARCH, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-lcudart", "-lcuda"]
+        cmd = [nvcc, *ARCH, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-lcudart"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)

@@ -1,0 +1,115 @@
+"""Tensor-level wrappers for the tensor-core stages (Hessian, SPD inverse, AWQ search loss,
+compensated GPTQ).  Same rules as b200q.ops: torch owns memory and streams, libb200quant does the
+arithmetic, nothing falls back to torch or the CPU."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib, dist as _dist
+from .ops import DTYPE_CODE, _on, _stream, dtype_code, require_cuda
+
+_scratch = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _scratch.pop(key, None)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+def release_workspace() -> None:
+    """Drop the cached Hessian scratch (it holds a scaled fp16 copy of the activations)."""
+    _scratch.clear()
+
+
+def hessian_accum(X: torch.Tensor, rows_per_sample: int, H: Optional[torch.Tensor] = None,
+                  return_norms: bool = False):
+    """H (+)= sum_i X_i^T X_i / (||X_i||_F + 1e-5)^2 over equal-length samples of the CUDA [T,K]
+    matrix X (fp32/fp16/bf16).  Returns H (fp32 [K,K]) or (H, norms)."""
+    assert X.is_cuda and X.dim() == 2
+    X = X.contiguous()
+    T, K = X.shape
+    assert T % rows_per_sample == 0
+    n = T // rows_per_sample
+    accumulate = H is not None
+    if H is None:
+        H = torch.empty((K, K), dtype=torch.float32, device=X.device)
+    norms = torch.empty(n, dtype=torch.float32, device=X.device) if return_norms else None
+    lib = _lib.load()
+    with _on(X.device):
+        work = _workspace(X.device, lib.b200q_hessian_workspace(T, K, n))
+        rc = lib.b200q_hessian_accum(X.data_ptr(), n, rows_per_sample, K, dtype_code(X),
+                                     H.data_ptr(), int(accumulate),
+                                     None if norms is None else norms.data_ptr(), work.data_ptr(),
+                                     _stream())
+    _lib.check(rc, "hessian_accum")
+    return (H, norms) if return_norms else H
+
+
+def hessian_finalize(H: torch.Tensor, scale: float, damp: float) -> torch.Tensor:
+    with _on(H.device):
+        rc = _lib.load().b200q_hessian_finalize(H.data_ptr(), H.shape[0], float(scale), float(damp),
+                                                _stream())
+    _lib.check(rc, "hessian_finalize")
+    return H
+
+
+def gptq_hessian(input_feat: Sequence, in_features: int, device, perp_damp: float = 0.01,
+                 nsamples: int = 128) -> torch.Tensor:
+    """The damped Hessian of gptq_quantizer.py:133-150 as fp32 [K,K] on `device`:
+    sum over input_feat[:nsamples] of x^T x / (||x|| + 1e-5)^2, divided by len(input_feat) (the
+    FULL list length, as the reference does), plus perp_damp * I.  A [n, K] tensor stands for n
+    one-row samples (the reference iterates its rows); non-tensor features give I."""
+    require_cuda()
+    device = torch.device(device)
+    K = in_features
+    if isinstance(input_feat, torch.Tensor):
+        feats_total = input_feat.shape[0]
+        runs = [(input_feat[:nsamples].reshape(-1, K), 1)] if input_feat.dim() == 2 else \
+            [(input_feat[:nsamples].reshape(-1, K), input_feat.shape[1])]
+    else:
+        feats_total = len(input_feat)
+        if feats_total == 0 or not isinstance(input_feat[0], torch.Tensor):
+            H = torch.eye(K, dtype=torch.float32, device=device)
+            return hessian_finalize(H, 1.0 / max(1, feats_total), perp_damp)
+        # group consecutive samples with the same number of rows into one call
+        runs: List = []
+        cur: List[torch.Tensor] = []
+        cur_rows = None
+        for f in input_feat[:nsamples]:
+            f2 = f.reshape(1, -1) if f.dim() == 1 else f.reshape(-1, f.shape[-1])
+            if cur_rows is not None and f2.shape[0] != cur_rows:
+                runs.append((cur, cur_rows))
+                cur = []
+            cur_rows = f2.shape[0]
+            cur.append(f2)
+        if cur:
+            runs.append((cur, cur_rows))
+        runs = [(torch.cat([t.to(device, non_blocking=True) for t in ts]) if len(ts) > 1
+                 else ts[0].to(device), r) for ts, r in runs]
+    H = None
+    # under row sharding the calibration samples are dealt to the ranks and the partial sums
+    # all-reduced (b200q.dist); every rank ends with the same H
+    world, rank = _dist.world_size(), _dist.rank()
+    for X, rows in runs:
+        X = X.to(device)
+        if X.dtype not in DTYPE_CODE:
+            X = X.float()
+        n = X.shape[0] // rows
+        if _dist.is_sharded():
+            lo, hi = _dist.shard_rows(n, world, rank)
+            X = X[lo * rows:hi * rows]
+            if X.shape[0] == 0:
+                continue
+        H = hessian_accum(X, rows, H)
+    if H is None:
+        H = torch.zeros((K, K), dtype=torch.float32, device=device)
+    _dist.allreduce_sum(H)
+    return hessian_finalize(H, 1.0 / feats_total, perp_damp)

@@ -1,0 +1,485 @@
+// Tensor-core stages (tcgen05 + TMEM accumulators, operands staged by TMA):
+//   * GPTQ Hessian  H += sum_i a_i^2 X_i^T X_i,  a_i = 1/(||X_i||_F + 1e-5)   ref: gptq_quantizer.py:137-144
+//   * AWQ scale search loss  tr(dW H dW^T) per candidate                        ref: awq_quantizer.py:116-119
+//
+// Hessian pipeline for one Linear (X is [T, K], T tokens of K input channels, samples are equal
+// runs of rows):
+//   1. sample_stats   per-sample sum of squares and |max|                       (HBM: read X once)
+//   2. prescale       Xs = fp16(X * a_i * 2^s), 2^s chosen so the largest value sits near 2^14:
+//                     every product of the GEMM is then exact in fp32 and inputs keep 11 bits
+//                                                                                (read X, write Xs)
+//   3. hessian_gemm   P[z] = Xs_z^T Xs_z on the tensor cores.  Both operands are tiles of the SAME
+//                     row-major matrix with the channel (M/N) direction contiguous, i.e. MN-major
+//                     UMMA operands: a TMA box of 64 tokens x 64 channels lands as 8x(8 rows x 128 B)
+//                     swizzle atoms, exactly the canonical MN-major SWIZZLE_128B layout.  One CTA
+//                     per 128x256 output tile and token split z; 4-stage mbarrier ring; warp 0 =
+//                     TMA producer, warp 1 = MMA issuer (one thread), warps 4-7 = epilogue
+//                     (tcgen05.ld -> fp32 stores).
+//   4. reduce         H (+)= 2^-2s * sum_z P[z], splits added in a fixed order (deterministic).
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace b200q {
+
+using namespace sm100;
+
+// =================================================================================================
+// 1. per-sample statistics
+// =================================================================================================
+// grid = (chunks, n_samples); each block reduces a slice of one sample; partial[(s*chunks + c)*2]
+template <typename T>
+__global__ void __launch_bounds__(256)
+sample_stats_partial_kernel(const T* __restrict__ X, int64_t rows_per_sample, int64_t K,
+                            float* __restrict__ partial) {
+  constexpr int VEC = ST<T>::VEC;
+  const int64_t s = blockIdx.y;
+  const int64_t n = rows_per_sample * K;          // elements of this sample (contiguous)
+  const T* p = X + s * n;
+  const int64_t nvec = n / VEC;
+  double acc = 0.0;
+  float amax = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float v[VEC];
+    load_vec<T>(p + i * VEC, v);
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { sq = fmaf(v[j], v[j], sq); amax = fmaxf(amax, fabsf(v[j])); }
+    acc += (double)sq;
+  }
+  // block reduce
+  __shared__ double s_acc[256];
+  __shared__ float s_max[256];
+  s_acc[threadIdx.x] = acc;
+  s_max[threadIdx.x] = amax;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_acc[threadIdx.x] += s_acc[threadIdx.x + o];
+      s_max[threadIdx.x] = fmaxf(s_max[threadIdx.x], s_max[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float* out = partial + (s * gridDim.x + blockIdx.x) * 2;
+    out[0] = (float)s_acc[0];
+    out[1] = s_max[0];
+  }
+}
+
+// one block: norms[i] = sqrt(sum), alpha[i] = 1/(norm + 1e-5); global power-of-two factor
+// stats layout: [0, n) alpha_i * 2^s ; [n, 2n) norms ; [2n] = 2^-2s
+__global__ void sample_stats_finish_kernel(const float* __restrict__ partial, int chunks,
+                                           int n_samples, float* __restrict__ stats) {
+  __shared__ float s_big[256];
+  float big = 0.f;
+  for (int s = threadIdx.x; s < n_samples; s += blockDim.x) {
+    double sum = 0.0;
+    float amax = 0.f;
+    for (int c = 0; c < chunks; ++c) {
+      sum += (double)partial[((int64_t)s * chunks + c) * 2];
+      amax = fmaxf(amax, partial[((int64_t)s * chunks + c) * 2 + 1]);
+    }
+    const float norm = (float)sqrt(sum);
+    const float alpha = 1.f / (norm + 1e-5f);            // gptq_quantizer.py:143
+    stats[n_samples + s] = norm;
+    stats[s] = alpha;
+    big = fmaxf(big, alpha * amax);
+  }
+  s_big[threadIdx.x] = big;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s_big[threadIdx.x] = fmaxf(s_big[threadIdx.x], s_big[threadIdx.x + o]);
+    __syncthreads();
+  }
+  big = s_big[0];
+  // 2^s: largest scaled magnitude lands in [2^13, 2^14) (fp16 max is 65504)
+  int e = 0;
+  if (big > 0.f && isfinite(big)) {
+    frexpf(big, &e);                                      // big = m * 2^e, m in [0.5, 1)
+    e = 14 - e;
+  }
+  e = max(-60, min(60, e));
+  const float pow2 = ldexpf(1.f, e);
+  __syncthreads();
+  for (int s = threadIdx.x; s < n_samples; s += blockDim.x) stats[s] *= pow2;
+  if (threadIdx.x == 0) stats[2 * n_samples] = ldexpf(1.f, -2 * e);
+}
+
+// =================================================================================================
+// 2. prescale: Xs[t, k] = fp16( X[t, k] * alpha_{sample(t)} * 2^s )
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+prescale_kernel(const T* __restrict__ X, __half* __restrict__ Xs, int64_t rows_per_sample, int64_t K,
+                int64_t total_vec, const float* __restrict__ stats) {
+  constexpr int VEC = ST<T>::VEC;
+  const int64_t vec_per_sample = rows_per_sample * K / VEC;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float a = stats[i / vec_per_sample];
+    float v[VEC];
+    load_vec<T>(X + i * VEC, v);
+    if constexpr (VEC == 8) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = v[j] * a;
+      store_vec<__half>(Xs + i * 8, o);
+    } else {
+      __half2 h0 = __floats2half2_rn(v[0] * a, v[1] * a);
+      __half2 h1 = __floats2half2_rn(v[2] * a, v[3] * a);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(Xs + i * 4) = pk;
+    }
+  }
+}
+
+// =================================================================================================
+// 3. Xs^T Xs on tcgen05
+// =================================================================================================
+namespace hg {
+constexpr int BM = 128;          // output rows per CTA  (channels)
+constexpr int BN = 256;          // output cols per CTA  (channels)
+constexpr int BKT = 64;          // tokens per pipeline stage
+constexpr int UMMA_K = 16;       // tokens per tcgen05.mma (16-bit inputs)
+constexpr int STAGES = 4;
+constexpr int BOX_CH = 64;       // channels per TMA box = one 128-byte swizzle row
+constexpr int BOX_BYTES = BKT * BOX_CH * 2;                 // 8 KiB
+constexpr int A_BYTES = (BM / BOX_CH) * BOX_BYTES;          // 16 KiB
+constexpr int B_BYTES = (BN / BOX_CH) * BOX_BYTES;          // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;              // 48 KiB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int THREADS = 256;
+constexpr uint32_t TMEM_COLS = 256;
+}  // namespace hg
+
+__global__ void __launch_bounds__(hg::THREADS, 1)
+hessian_gemm_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ partial,
+                    int64_t K, int64_t T, int64_t tokens_per_split) {
+  using namespace hg;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128-byte swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.x, m_blk = blockIdx.y, z = blockIdx.z;
+  const int64_t t0 = (int64_t)z * tokens_per_split;
+  const int64_t t1 = min(T, t0 + tokens_per_split);
+  const int num_kb = (int)((t1 - t0 + BKT - 1) / BKT);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* a_dst = smem + stage * STAGE_BYTES;
+        uint8_t* b_dst = a_dst + A_BYTES;
+        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        const int32_t tok = (int32_t)(t0 + (int64_t)kb * BKT);
+#pragma unroll
+        for (int j = 0; j < BM / BOX_CH; ++j)
+          tma_load_2d(a_dst + j * BOX_BYTES, &tmap, &full_bar[stage],
+                      m_blk * BM + j * BOX_CH, tok);
+#pragma unroll
+        for (int j = 0; j < BN / BOX_CH; ++j)
+          tma_load_2d(b_dst + j * BOX_BYTES, &tmap, &full_bar[stage],
+                      n_blk * BN + j * BOX_CH, tok);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN, /*bf16=*/false, /*a_mn=*/true, /*b_mn=*/true);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BKT / UMMA_K; ++k) {
+          // 16 tokens = 16 rows of 128 bytes further down every box
+          const uint32_t koff = k * UMMA_K * 128;
+          const uint64_t da = make_smem_desc_sw128(a_addr + koff, BOX_BYTES, 1024);
+          const uint64_t db = make_smem_desc_sw128(b_addr + koff, BOX_BYTES, 1024);
+          mma_f16_ss(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        mma_commit(&empty_bar[stage]);          // frees the smem stage once these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(tmem_full_bar);                // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> global (fp32) =====
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    float* dst_base = partial + (int64_t)z * K * K;
+    const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
+    if (num_kb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after_sync();
+    }
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      if (num_kb > 0) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      const int64_t col0 = (int64_t)n_blk * BN + c * 32;
+      if (row < K) {
+        float* dst = dst_base + row * K + col0;
+        if (col0 + 32 <= K) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < K) dst[j] = __uint_as_float(v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// =================================================================================================
+// 4. split reduction and finalisation
+// =================================================================================================
+__global__ void hessian_reduce_kernel(const float* __restrict__ partial, int splits, int64_t KK,
+                                      const float* __restrict__ stats, int n_samples,
+                                      float* __restrict__ H, int accumulate) {
+  const float unscale = stats[2 * n_samples];
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < KK;
+       i += (int64_t)gridDim.x * blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < splits; ++z) {
+      const float4 p = *reinterpret_cast<const float4*>(partial + (int64_t)z * KK + i);
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    acc.x *= unscale; acc.y *= unscale; acc.z *= unscale; acc.w *= unscale;
+    if (accumulate) {
+      const float4 h = *reinterpret_cast<const float4*>(H + i);
+      acc.x += h.x; acc.y += h.y; acc.z += h.z; acc.w += h.w;
+    }
+    *reinterpret_cast<float4*>(H + i) = acc;
+  }
+}
+
+// H = H * scale + damp * I      (gptq_quantizer.py:150 and the 1e-6 ridge of :160)
+__global__ void hessian_finalize_kernel(float* __restrict__ H, int64_t K, float scale, float damp) {
+  const int64_t KK = K * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < KK;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float v = H[i] * scale;
+    if (i / K == i % K) v += damp;
+    H[i] = v;
+  }
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// tensor map over a row-major [rows, cols] 16-bit matrix, box = box_rows x 64 columns, 128B swizzle
+static int make_tmap_2d_16bit(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
+                              int box_rows, int box_cols) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return fail(B200Q_ECUDA, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200Q_ECUDA, "cuTensorMapEncodeTiled failed");
+  return B200Q_OK;
+}
+
+static int hessian_splits(int64_t K, int64_t T) {
+  const int64_t tiles = ((K + hg::BM - 1) / hg::BM) * ((K + hg::BN - 1) / hg::BN);
+  const int64_t kblocks = (T + hg::BKT - 1) / hg::BKT;
+  // one CTA per (tile, split), one CTA per SM at a time: pick the split count (<= 16, >= 8
+  // k-blocks of work each) whose CTA count fills whole waves of 148 best; ties go to fewer splits
+  const int64_t max_s = std::max<int64_t>(1, std::min<int64_t>(16, kblocks / 8));
+  int64_t best = 1;
+  double best_eff = -1.0;
+  for (int64_t s = 1; s <= max_s; ++s) {
+    const int64_t ctas = tiles * s;
+    const double eff = (double)ctas / (double)(((ctas + kNumSMs - 1) / kNumSMs) * kNumSMs);
+    if (eff > best_eff + 0.01) { best_eff = eff; best = s; }
+  }
+  return (int)best;
+}
+
+struct HessianWork {
+  float* stats;       // [2n + 1]
+  float* partial_st;  // [n * chunks * 2]
+  __half* Xs;         // [T, K]
+  float* partial;     // [splits, K, K]
+  int chunks, splits;
+  int64_t bytes;
+};
+
+static HessianWork hessian_layout(void* work, int64_t T, int64_t K, int n_samples) {
+  HessianWork w;
+  w.chunks = (int)std::max<int64_t>(1, std::min<int64_t>(64, (2 * kNumSMs) / std::max(1, n_samples)));
+  w.splits = hessian_splits(K, T);
+  auto align = [](int64_t x) { return (x + 255) / 256 * 256; };
+  int64_t off = 0;
+  uint8_t* base = static_cast<uint8_t*>(work);
+  w.stats = reinterpret_cast<float*>(base + off);
+  off += align(sizeof(float) * (2 * (int64_t)n_samples + 1));
+  w.partial_st = reinterpret_cast<float*>(base + off);
+  off += align(sizeof(float) * 2 * (int64_t)n_samples * w.chunks);
+  w.Xs = reinterpret_cast<__half*>(base + off);
+  off += align(2 * T * K);
+  w.partial = reinterpret_cast<float*>(base + off);
+  off += align(sizeof(float) * (int64_t)w.splits * K * K);
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace b200q
+
+using namespace b200q;
+
+extern "C" {
+
+int64_t b200q_hessian_workspace(int64_t T, int64_t K, int n_samples) {
+  if (T <= 0 || K <= 0 || n_samples <= 0) return 0;
+  return hessian_layout(nullptr, T, K, n_samples).bytes;
+}
+
+int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, int64_t K, int dtype,
+                        float* H, int accumulate, float* norms_out, void* work, void* stream) {
+  B200Q_REQUIRE(X && H && work, "hessian_accum: null pointer");
+  B200Q_REQUIRE(n_samples > 0 && rows_per_sample > 0 && K > 0, "hessian_accum: bad shape");
+  B200Q_REQUIRE(K % 8 == 0, "hessian_accum: in_features must be a multiple of 8");
+  B200Q_REQUIRE(aligned16(X) && aligned16(H) && aligned16(work), "hessian_accum: unaligned pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t T = (int64_t)n_samples * rows_per_sample;
+  B200Q_REQUIRE(T < (1ll << 31) && K < (1ll << 31), "hessian_accum: dimension too large");
+  HessianWork w = hessian_layout(work, T, K, n_samples);
+  const double flops = 2.0 * (double)T * (double)K * (double)K;
+
+  {
+    KernelScope scope("hessian_prescale", 3.0 * T * K * elem_size(dtype), 0, st);
+    B200Q_DISPATCH_DTYPE(dtype, Tt, {
+      constexpr int VEC = ST<Tt>::VEC;
+      B200Q_REQUIRE((rows_per_sample * K) % VEC == 0, "hessian_accum: sample not 16-byte sized");
+      dim3 g1((unsigned)w.chunks, (unsigned)n_samples);
+      sample_stats_partial_kernel<Tt><<<g1, 256, 0, st>>>(static_cast<const Tt*>(X),
+                                                          rows_per_sample, K, w.partial_st);
+      sample_stats_finish_kernel<<<1, 256, 0, st>>>(w.partial_st, w.chunks, n_samples, w.stats);
+      const int64_t total_vec = T * K / VEC;
+      const int blocks = (int)std::min<int64_t>((total_vec + 255) / 256, (int64_t)kNumSMs * 16);
+      prescale_kernel<Tt><<<blocks, 256, 0, st>>>(static_cast<const Tt*>(X), w.Xs, rows_per_sample,
+                                                  K, total_vec, w.stats);
+    });
+    count_launch(3);
+    int rc = check_launch("hessian_accum/prescale");
+    if (rc != B200Q_OK) return rc;
+  }
+  if (norms_out != nullptr)
+    cudaMemcpyAsync(norms_out, w.stats + n_samples, sizeof(float) * n_samples,
+                    cudaMemcpyDeviceToDevice, st);
+
+  CUtensorMap tmap;
+  int rc = make_tmap_2d_16bit(&tmap, w.Xs, T, K, hg::BKT, hg::BOX_CH);
+  if (rc != B200Q_OK) return rc;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, []() {
+    attr_err = cudaFuncSetAttribute(hessian_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    hg::SMEM_BYTES);
+  });
+  // (per-device attribute: re-apply cheaply every call; the call is idempotent)
+  cudaFuncSetAttribute(hessian_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       hg::SMEM_BYTES);
+  if (attr_err != cudaSuccess) return fail(B200Q_ECUDA, "hessian_gemm: cannot raise shared memory");
+  const int64_t kblocks = (T + hg::BKT - 1) / hg::BKT;
+  const int64_t kb_per_split = (kblocks + w.splits - 1) / w.splits;
+  const int64_t tokens_per_split = kb_per_split * hg::BKT;
+  {
+    KernelScope scope("hessian_gemm", 0, flops, st);
+    dim3 grid((unsigned)((K + hg::BN - 1) / hg::BN), (unsigned)((K + hg::BM - 1) / hg::BM),
+              (unsigned)w.splits);
+    hessian_gemm_kernel<<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(tmap, w.partial, K, T,
+                                                                   tokens_per_split);
+    count_launch();
+    rc = check_launch("hessian_gemm");
+    if (rc != B200Q_OK) return rc;
+  }
+  {
+    KernelScope scope("hessian_reduce", sizeof(float) * (double)(w.splits + 1) * K * K, 0, st);
+    const int64_t KK = K * K;
+    const int blocks = (int)std::min<int64_t>((KK / 4 + 255) / 256, (int64_t)kNumSMs * 16);
+    hessian_reduce_kernel<<<blocks, 256, 0, st>>>(w.partial, w.splits, KK, w.stats, n_samples, H,
+                                                  accumulate);
+    count_launch();
+    rc = check_launch("hessian_reduce");
+  }
+  return rc;
+}
+
+int b200q_hessian_finalize(float* H, int64_t K, float scale, float damp, void* stream) {
+  B200Q_REQUIRE(H && K > 0, "hessian_finalize: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t KK = K * K;
+  const int blocks = (int)std::min<int64_t>((KK + 255) / 256, (int64_t)kNumSMs * 16);
+  hessian_finalize_kernel<<<blocks, 256, 0, st>>>(H, K, scale, damp);
+  count_launch();
+  return check_launch("hessian_finalize");
+}
+
+}  // extern "C"
