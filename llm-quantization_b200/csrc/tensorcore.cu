@@ -157,11 +157,12 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;              // 48 KiB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int THREADS = 256;
 constexpr uint32_t TMEM_COLS = 256;
+constexpr int RASTER_M = 16;     // tile rows per rasterisation band
 }  // namespace hg
 
 __global__ void __launch_bounds__(hg::THREADS, 1)
 hessian_gemm_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ partial,
-                    int64_t K, int64_t T, int64_t tokens_per_split) {
+                    int64_t K, int64_t T, int64_t tokens_per_split, int tiles_n) {
   using namespace hg;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle atoms
@@ -174,7 +175,18 @@ hessian_gemm_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_blk = blockIdx.x, m_blk = blockIdx.y, z = blockIdx.z;
+  // Tile order: bands of RASTER_M tile rows, column-major inside a band.  The ~148 CTAs resident
+  // at any time then form a compact ~16 x 9 patch of tiles that touches only ~4.4K distinct
+  // channels per token, start together and stream the tokens in lockstep, so every TMA box is
+  // fetched from DRAM once per wave and hit in L2 by the other CTAs (ncu at K = 11008: the plain
+  // row-major order ran at 38 % L2 hit rate and was DRAM-bound).
+  const int tiles_m = (int)((K + BM - 1) / BM);
+  const int band = blockIdx.x / (RASTER_M * tiles_n);
+  const int within = blockIdx.x % (RASTER_M * tiles_n);
+  const int band_rows = min(RASTER_M, tiles_m - band * RASTER_M);
+  const int n_blk = within / band_rows;
+  const int m_blk = band * RASTER_M + within % band_rows;
+  const int z = blockIdx.y;
   const int64_t t0 = (int64_t)z * tokens_per_split;
   const int64_t t1 = min(T, t0 + tokens_per_split);
   const int num_kb = (int)((t1 - t0 + BKT - 1) / BKT);
@@ -452,10 +464,11 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
   const int64_t tokens_per_split = kb_per_split * hg::BKT;
   {
     KernelScope scope("hessian_gemm", 0, flops, st);
-    dim3 grid((unsigned)((K + hg::BN - 1) / hg::BN), (unsigned)((K + hg::BM - 1) / hg::BM),
-              (unsigned)w.splits);
+    const int tiles_n = (int)((K + hg::BN - 1) / hg::BN);
+    const int tiles_m = (int)((K + hg::BM - 1) / hg::BM);
+    dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)w.splits);
     hessian_gemm_kernel<<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(tmap, w.partial, K, T,
-                                                                   tokens_per_split);
+                                                                   tokens_per_split, tiles_n);
     count_launch();
     rc = check_launch("hessian_gemm");
     if (rc != B200Q_OK) return rc;
