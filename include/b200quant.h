@@ -180,6 +180,17 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
  * perp_damp) and :160 (scale = 1, damp = 1e-6) */
 int b200q_hessian_finalize(float* H, int64_t K, float scale, float damp, void* stream);
 
+/* ---- damped SPD inverse ------------------------------------------------------------------
+ * For symmetric positive definite H (fp32 [K,K]): Hinv = inv(H) and/or U = the upper Cholesky
+ * factor of inv(H) (U^T U = inv(H)), via blocked Cholesky, triangular inverse and L^-T L^-1.
+ * ref: gptq_quantizer.py:160-165 (torch.linalg.inv(H + 1e-6 I); the caller adds the ridge with
+ * b200q_hessian_finalize).  U is what the error-compensated column loop consumes.
+ * Either of Hinv / U may be NULL.  work: b200q_spd_inverse_workspace(K) bytes.  info (device
+ * int, optional, zero it first): 0 = ok, j > 0 = pivot j was not positive. */
+int64_t b200q_spd_inverse_workspace(int64_t K);
+int b200q_spd_inverse(const float* H, float* Hinv, float* U, int64_t K, void* work, int* info,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

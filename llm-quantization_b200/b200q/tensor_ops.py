@@ -61,6 +61,35 @@ def hessian_finalize(H: torch.Tensor, scale: float, damp: float) -> torch.Tensor
     return H
 
 
+def spd_inverse(H: torch.Tensor, ridge: float = 0.0, want_inverse: bool = True,
+                want_upper: bool = False):
+    """inv(H + ridge I) (and/or the upper Cholesky factor U of it, U^T U = inverse) for a CUDA
+    fp32 SPD matrix.  Returns Hinv, U or (Hinv, U).  Under row sharding rank 0 computes and the
+    result is broadcast (the inverse is shared by all row shards)."""
+    assert H.is_cuda and H.dtype == torch.float32 and H.dim() == 2 and H.shape[0] == H.shape[1]
+    K = H.shape[0]
+    lib = _lib.load()
+    Hinv = torch.empty_like(H) if want_inverse else None
+    U = torch.empty_like(H) if want_upper else None
+    if not _dist.is_sharded() or _dist.rank() == 0:
+        A = H.contiguous()
+        if ridge != 0.0:
+            A = hessian_finalize(A.clone(), 1.0, ridge)
+        with _on(H.device):
+            work = _workspace(H.device, lib.b200q_spd_inverse_workspace(K))
+            info = torch.zeros(1, dtype=torch.int32, device=H.device)
+            rc = lib.b200q_spd_inverse(A.data_ptr(), None if Hinv is None else Hinv.data_ptr(),
+                                       None if U is None else U.data_ptr(), K, work.data_ptr(),
+                                       info.data_ptr(), _stream())
+        _lib.check(rc, "spd_inverse")
+    for t in (Hinv, U):
+        if t is not None:
+            _dist.broadcast(t, 0)
+    if Hinv is not None and U is not None:
+        return Hinv, U
+    return Hinv if Hinv is not None else U
+
+
 def gptq_hessian(input_feat: Sequence, in_features: int, device, perp_damp: float = 0.01,
                  nsamples: int = 128) -> torch.Tensor:
     """The damped Hessian of gptq_quantizer.py:133-150 as fp32 [K,K] on `device`:
