@@ -191,6 +191,18 @@ int64_t b200q_spd_inverse_workspace(int64_t K);
 int b200q_spd_inverse(const float* H, float* Hinv, float* U, int64_t K, void* work, int* info,
                       void* stream);
 
+/* ---- GPTQ with error compensation (opt-in; NOT what the reference computes) ---------------
+ * The blockwise column loop gptq_quantizer.py:173-197 sketches and then skips ("we skip error
+ * compensation"), as in Frantar et al. 2022 Alg. 1: per column quantise with the asymmetric group
+ * grid of pseudo_quantize_tensor, propagate e = (w - q)/U[j,j] into the remaining columns of the
+ * 128-column block, then push the block's errors into all later columns with one rank-128 GEMM.
+ * W: fp32 [N,K], overwritten; Q: fp32 [N,K] result; U: upper Cholesky factor of inv(H) from
+ * b200q_spd_inverse.  group: 128, a multiple of 128, or <= 0 (per row).  blocksize must be 128.
+ * work: b200q_gptq_compensated_workspace(N, K) bytes. */
+int64_t b200q_gptq_compensated_workspace(int64_t N, int64_t K);
+int b200q_gptq_compensated(float* W, float* Q, const float* U, int64_t N, int64_t K, int64_t group,
+                           int n_bit, int blocksize, void* work, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,9 @@ SIGNATURES = {
     "b200q_hessian_finalize": (C.c_int, [c_fp, c_i64, C.c_float, C.c_float, c_vp]),
     "b200q_spd_inverse_workspace": (c_i64, [c_i64]),
     "b200q_spd_inverse": (C.c_int, [c_fp, c_fp, c_fp, c_i64, c_vp, c_vp, c_vp]),
+    "b200q_gptq_compensated_workspace": (c_i64, [c_i64, c_i64]),
+    "b200q_gptq_compensated": (C.c_int, [c_fp, c_fp, c_fp, c_i64, c_i64, c_i64, C.c_int, C.c_int,
+                                         c_vp, c_vp]),
     "b200q_pot_quant": (C.c_int, [c_vp, c_vp, c_vp, c_fp, c_vp, c_i64, c_i64, C.c_int,
                                   C.POINTER(C.c_float), C.c_int, C.c_int, c_vp]),
     "b200q_apot_quant": (C.c_int, [c_vp, c_vp, c_vp, c_fp, c_vp, c_i64, c_i64,

@@ -90,6 +90,31 @@ def spd_inverse(H: torch.Tensor, ridge: float = 0.0, want_inverse: bool = True,
     return Hinv if Hinv is not None else U
 
 
+def gptq_compensated(W: torch.Tensor, H: torch.Tensor, n_bit: int, group: int, blocksize: int = 128,
+                     perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Error-compensated GPTQ of a CUDA [N,K] weight given its damped Hessian H (fp32 [K,K]).
+    `perm` (act-order) permutes the columns before and restores them after, as GPTQ does."""
+    assert W.is_cuda and W.dim() == 2 and H.shape == (W.shape[1], W.shape[1])
+    N, K = W.shape
+    Wf = W.float()
+    if perm is not None:
+        Wf = Wf[:, perm]
+        H = H[perm][:, perm]
+    Wf = Wf.contiguous().clone() if Wf.data_ptr() == W.data_ptr() else Wf.contiguous()
+    U = spd_inverse(H.contiguous(), ridge=1e-6, want_inverse=False, want_upper=True)
+    Q = torch.empty_like(Wf)
+    lib = _lib.load()
+    with _on(W.device):
+        work = torch.empty(lib.b200q_gptq_compensated_workspace(N, K), dtype=torch.uint8,
+                           device=W.device)
+        rc = lib.b200q_gptq_compensated(Wf.data_ptr(), Q.data_ptr(), U.data_ptr(), N, K, group, n_bit,
+                                        blocksize, work.data_ptr(), _stream())
+    _lib.check(rc, "gptq_compensated")
+    if perm is not None:
+        Q = Q[:, torch.argsort(perm)]
+    return Q.to(W.dtype)
+
+
 def gptq_hessian(input_feat: Sequence, in_features: int, device, perp_damp: float = 0.01,
                  nsamples: int = 128) -> torch.Tensor:
     """The damped Hessian of gptq_quantizer.py:133-150 as fp32 [K,K] on `device`:

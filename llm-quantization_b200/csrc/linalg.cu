@@ -269,6 +269,120 @@ static int cholesky_and_inverse(cudaStream_t st, const LinalgWork& w, int64_t K,
   return check_launch("cholesky_and_inverse");
 }
 
+// =================================================================================================
+// Error-compensated GPTQ column loop (opt-in; the reference sketches it in gptq_quantizer.py:173-197
+// and then skips the compensation).  Frantar et al. 2022, Alg. 1, with the asymmetric per-group
+// grid of pseudo_quantize_tensor:  for each column j:  q = quant(w_j);  e = (w_j - q) / U[j,j];
+// w_{j+1..block end} -= e * U[j, j+1..];  after a block of 128 columns the accumulated errors are
+// pushed into all later columns with one GEMM (the lazy rank-128 update).
+// Rows are independent: ONE WARP owns one row of the 128-column block, 4 columns per lane in
+// registers; the column being quantised is broadcast with a shuffle, every lane applies the rank-1
+// update to its own columns from the U block held in shared memory.
+// =================================================================================================
+namespace gc {
+constexpr int B = 128;   // block of columns = lazy-update rank
+}
+
+// scale / zero-point of pseudo_quantize_tensor from a (min, max) pair    quantization_utils.py:395-396
+__device__ __forceinline__ void asym_params(float mx, float mn, float maxint, float& scale,
+                                            float& zp) {
+  scale = __fdiv_rn(fmaxf(mx - mn, 1e-5f), maxint);
+  zp = clampf(-rintf(__fdiv_rn(mn, scale)), 0.f, maxint);
+}
+
+// per-row (min,max) over columns [c0, c0+G) -> scale/zero   (groups wider than one block)
+__global__ void __launch_bounds__(256)
+row_range_params_kernel(const float* __restrict__ W, int64_t N, int64_t K, int64_t c0, int64_t G,
+                        float maxint, float* __restrict__ scales, float* __restrict__ zeros) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t c1 = min(K, c0 + G);
+  for (int64_t r = warp; r < N; r += nwarps) {
+    float mx = -INFINITY, mn = INFINITY;
+    for (int64_t c = c0 + lane; c < c1; c += 32) {
+      const float v = W[r * K + c];
+      mx = fmaxf(mx, v); mn = fminf(mn, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if (lane == 0) asym_params(mx, mn, maxint, scales[r], zeros[r]);
+  }
+}
+
+template <bool OWN_GROUP>
+__global__ void __launch_bounds__(256)
+gptq_block_kernel(float* __restrict__ W, float* __restrict__ Q, float* __restrict__ Err,
+                  const float* __restrict__ U, int64_t N, int64_t K, int64_t c0, int nb,
+                  float maxint, const float* __restrict__ scales, const float* __restrict__ zeros) {
+  extern __shared__ float Ub[];            // [B][B+1] block of U; row j holds U[c0+j, c0+...]
+  constexpr int LD = gc::B + 1;
+  for (int i = threadIdx.x; i < gc::B * gc::B; i += blockDim.x) {
+    const int r = i / gc::B, c = i % gc::B;
+    Ub[r * LD + c] = (r < nb && c < nb) ? U[(c0 + r) * K + (c0 + c)] : (r == c ? 1.f : 0.f);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < N; r += nwarps) {
+    float w[4], qv[4], ev[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      w[i] = (c < nb) ? W[r * K + c0 + c] : 0.f;
+      qv[i] = 0.f; ev[i] = 0.f;
+    }
+    float scale, zp;
+    if constexpr (OWN_GROUP) {
+      float mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (lane + 32 * i < nb) { mx = fmaxf(mx, w[i]); mn = fminf(mn, w[i]); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      }
+      asym_params(mx, mn, maxint, scale, zp);
+    } else {
+      scale = scales[r]; zp = zeros[r];
+    }
+    const Divisor sd(scale);
+#pragma unroll
+    for (int slot = 0; slot < 4; ++slot) {
+      for (int o = 0; o < 32; ++o) {
+        const int j = slot * 32 + o;
+        if (j >= nb) break;
+        const float wj = __shfl_sync(0xffffffffu, w[slot], o);
+        const float code = clampf(rintf(sd.div(wj)) + zp, 0.f, maxint);
+        const float q = (code - zp) * scale;
+        const float e = __fdiv_rn(wj - q, Ub[j * LD + j]);
+        if (lane == o) { qv[slot] = q; ev[slot] = e; }
+        const float* urow = Ub + j * LD;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = lane + 32 * i;
+          if (c > j) w[i] = fmaf(-e, urow[c], w[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nb) {
+        Q[r * K + c0 + c] = qv[i];
+        Err[r * gc::B + c] = ev[i];
+      } else {
+        Err[r * gc::B + c] = 0.f;
+      }
+    }
+  }
+}
+
 }  // namespace b200q
 
 using namespace b200q;
@@ -314,6 +428,58 @@ int b200q_spd_inverse(const float* H, float* Hinv, float* U, int64_t K, void* wo
     rc = check_launch("spd_inverse/upper");
   }
   return rc;
+}
+
+
+int64_t b200q_gptq_compensated_workspace(int64_t N, int64_t K) {
+  if (N <= 0 || K <= 0) return 0;
+  return (int64_t)sizeof(float) * (N * gc::B + 2 * N) + 512;
+}
+
+// W (fp32 [N,K], destroyed) -> Q (fp32 [N,K]) with U = upper Cholesky factor of H^-1.
+// group: 128 (== block), a larger multiple of 128, or <= 0 (one group per row).
+int b200q_gptq_compensated(float* W, float* Q, const float* U, int64_t N, int64_t K, int64_t group,
+                           int n_bit, int blocksize, void* work, void* stream) {
+  B200Q_REQUIRE(W && Q && U && work && N > 0 && K > 0, "gptq_compensated: bad argument");
+  B200Q_REQUIRE(n_bit >= 1 && n_bit <= 16, "gptq_compensated: n_bit must be in [1,16]");
+  if (blocksize != gc::B)
+    return fail(B200Q_EUNSUPPORTED, "gptq_compensated: blocksize must be 128");
+  const int64_t G = group > 0 ? group : K;
+  if (!(G == gc::B || G % gc::B == 0 || G >= K))
+    return fail(B200Q_EUNSUPPORTED, "gptq_compensated: group must be 128, a multiple of 128 or per-row");
+  B200Q_REQUIRE(K % G == 0 || G >= K, "gptq_compensated: in_features not divisible by group size");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KernelScope scope("gptq_compensated", 2.0 * N * K * 4, (double)N * K * K, st);
+  float* Err = static_cast<float*>(work);
+  float* scales = Err + N * gc::B;
+  float* zeros = scales + N;
+  const float maxint = (float)((1 << n_bit) - 1);
+  const int smem = gc::B * (gc::B + 1) * (int)sizeof(float);
+  cudaFuncSetAttribute(gptq_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(gptq_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int blocks = (int)std::min<int64_t>((N + 7) / 8, (int64_t)kNumSMs * 2);
+  for (int64_t c0 = 0; c0 < K; c0 += gc::B) {
+    const int nb = (int)std::min<int64_t>(gc::B, K - c0);
+    if (G == gc::B) {
+      gptq_block_kernel<true><<<blocks, 256, smem, st>>>(W, Q, Err, U, N, K, c0, nb, maxint, nullptr,
+                                                         nullptr);
+    } else {
+      if (c0 % G == 0) {
+        row_range_params_kernel<<<blocks, 256, 0, st>>>(W, N, K, c0, G, maxint, scales, zeros);
+        count_launch();
+      }
+      gptq_block_kernel<false><<<blocks, 256, smem, st>>>(W, Q, Err, U, N, K, c0, nb, maxint, scales,
+                                                          zeros);
+    }
+    count_launch();
+    const int64_t rest = K - (c0 + nb);
+    if (rest > 0) {
+      // W[:, c1:] -= Err[N, nb] * U[c0:c1, c1:]          (lazy rank-128 update)
+      sgemm<false, false>(st, (int)N, (int)rest, nb, -1.f, Err, gc::B, U + c0 * K + (c0 + nb), K, 1.f,
+                          W + (c0 + nb), K);
+    }
+  }
+  return check_launch("gptq_compensated");
 }
 
 }  // extern "C"

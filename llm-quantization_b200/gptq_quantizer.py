@@ -34,7 +34,7 @@ from b200q import dist as _dist  # noqa: E402
 from b200q import pipeline as _pipeline  # noqa: E402
 
 MODE = "parity"
-BUILD_HESSIAN = False  # flipped on once the tensor-core stages land
+BUILD_HESSIAN = True
 
 
 # ==================================================================================================

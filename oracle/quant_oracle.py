@@ -323,13 +323,16 @@ def awq_search_losses(W: torch.Tensor, H: torch.Tensor, salient: torch.Tensor, n
 
 @torch.no_grad()
 def gptq_compensated(W: torch.Tensor, H: torch.Tensor, n_bit: int, group: int,
-                     blocksize: int = 128) -> torch.Tensor:
+                     blocksize: int = 128, perm: Optional[torch.Tensor] = None) -> torch.Tensor:
     """GPTQ (Frantar et al. 2022, Alg. 1) with the asymmetric per-group grid of
     pseudo_quantize_tensor: the loop gptq_quantizer.py:173-197 sketches and then skips.
     H must already include the damping.  float64 reference arithmetic."""
     Wd = W.double().clone()
     N, K = Wd.shape
     G = group if group > 0 else K
+    if perm is not None:
+        inv = torch.argsort(perm)
+        return gptq_compensated(W[:, perm], H[perm][:, perm], n_bit, group, blocksize)[:, inv]
     Hinv = torch.linalg.inv(H.double())
     U = torch.linalg.cholesky(Hinv, upper=True)
     qmax = 2 ** n_bit - 1
