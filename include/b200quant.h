@@ -172,10 +172,12 @@ int b200q_apot_quant(const void* w, void* out, uint8_t* level_idx, float* best_s
  * H is fp32 [K,K], fully written (both triangles); accumulate != 0 adds to its contents (ragged
  * sample lists are fed as several calls).  norms_out (optional, fp32 [n_samples]) receives
  * ||X_i||_F.  work: b200q_hessian_workspace(T, K, n_samples) bytes of device scratch.
- * K must be a multiple of 8. */
+ * K must be a multiple of 8.  normalize = 0 drops the per-sample factor (plain X^T X, the
+ * Gram matrix the AWQ search measures its reconstruction error with). */
 int64_t b200q_hessian_workspace(int64_t T, int64_t K, int n_samples);
 int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, int64_t K, int dtype,
-                        float* H, int accumulate, float* norms_out, void* work, void* stream);
+                        int normalize, float* H, int accumulate, float* norms_out, void* work,
+                        void* stream);
 /* H = H * scale + damp * I     ref: gptq_quantizer.py:150 (scale = 1/len(input_feat), damp =
  * perp_damp) and :160 (scale = 1, damp = 1e-6) */
 int b200q_hessian_finalize(float* H, int64_t K, float scale, float damp, void* stream);
@@ -202,6 +204,20 @@ int b200q_spd_inverse(const float* H, float* Hinv, float* U, int64_t K, void* wo
 int64_t b200q_gptq_compensated_workspace(int64_t N, int64_t K);
 int b200q_gptq_compensated(float* W, float* Q, const float* U, int64_t N, int64_t K, int64_t group,
                            int n_bit, int blocksize, void* work, void* stream);
+
+/* ---- AWQ scale search (tcgen05) -----------------------------------------------------------
+ * loss[c] += sum_rows dW_c H dW_c^T = ||(Q_c(W) - W) X^T||_F^2 for H = X^T X, for every candidate
+ * scale factor sf[c]; Q_c is awq_quantize_model_weight's arithmetic with scale_factor = sf[c] on
+ * the columns flagged in `salient` (uint8 [K]).
+ * ref: awq_quantizer.py:88-126 — a stub returning the midpoint; its docstring (:116-119) states
+ * this search.  PARITY UNPINNED.  Stage 1 writes all candidates' dW as bf16 from one read of W,
+ * stage 2 is one K-major bf16 GEMM over the stacked candidates with <dW H, dW> fused into the
+ * epilogue.  group must be 128 and K a multiple of 128.  loss is accumulated into (zero it; row
+ * shards on several GPUs all-reduce it).  sf_host: n_cand <= 32 floats on the host. */
+int64_t b200q_awq_search_workspace(int64_t N, int64_t K, int n_cand);
+int b200q_awq_search_loss(const void* W, int64_t N, int64_t K, int64_t group, int n_bit,
+                          const uint8_t* salient, const float* sf_host, int n_cand, const float* H,
+                          int dtype, void* work, float* loss, void* stream);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,18 @@ def _feat_matrix(feats, device) -> torch.Tensor:
     return stacked.to(device, non_blocking=True)
 
 
+def _stat_rows(feats: List[torch.Tensor], device) -> torch.Tensor:
+    """[n, K] matrix of per-batch mean|x| rows from a feature list whose entries are either such
+    vectors already (1-D) or raw [tokens, K] activations (reduced by the act_meanabs kernel)."""
+    rows = []
+    for f in feats:
+        if f.dim() == 1:
+            rows.append(f.to(device))
+        else:
+            rows.append(_ops.act_meanabs(_ops.to_device(f)).to(f.dtype))
+    return torch.stack(rows)
+
+
 def _importance(feats, device) -> torch.Tensor:
     """sum(list of [K] tensors).float(), evaluated left to right in the tensors' own dtype."""
     return _ops.seq_sum_rows(_feat_matrix(feats, device))
@@ -97,21 +109,30 @@ def awq_search_scale_factor(
         print(f"  -> Using scale factor: {best:.3f}")
         return best
     from b200q import tensor_ops as _tops
+    from b200q import dist as _dist
     candidates = torch.linspace(float(lo), float(hi), int(n_grid), dtype=torch.float64).tolist()
     total = None
     for name, module in model.named_modules():
         if not isinstance(module, nn.Linear) or name not in input_feat:
             continue
         W = _ops.to_device(module.weight.data)
+        K = W.shape[1]
         feats = input_feat[name]
-        salient = _salient_channels(_importance([f.abs().reshape(-1, f.shape[-1]).mean(0)
-                                                 if f.dim() > 1 else f for f in feats], W.device),
-                                    protect_ratio)
-        loss = _tops.awq_search_losses(W, feats, salient, w_bit, q_group_size, candidates)
+        # 2-D [tokens, K] features are raw activations: their per-batch mean|x| is the statistic
+        # the quantizer ranks channels by (quantization_utils.py:231); 1-D features already are it
+        if isinstance(feats, torch.Tensor):
+            stat_rows = feats if feats.dim() == 2 else _stat_rows(list(feats), W.device)
+        else:
+            stat_rows = _stat_rows(feats, W.device)
+        n_protect = max(1, int(K * protect_ratio))
+        mask = _ops.salient_mask(_feat_matrix(stat_rows, W.device), n_protect)
+        H = _tops.gram_matrix(feats, K, W.device)
+        loss = _tops.awq_search_losses(W, H, mask, w_bit, q_group_size, candidates)
         total = loss if total is None else total + loss
     if total is None:
         best = (lo + hi) / 2.0
     else:
+        _dist.allreduce_sum(total)
         best = candidates[int(torch.argmin(total).item())]
     print(f"  -> Using scale factor: {best:.3f}")
     return float(best)

@@ -295,6 +295,21 @@ def awq_layer(W: torch.Tensor, feats: torch.Tensor, n_bit: int, group: int, n_pr
     return (out, mask) if return_mask else out
 
 
+def salient_mask(feats: torch.Tensor, n_protect: int) -> torch.Tensor:
+    """uint8 [K] mask of the n_protect channels with the largest summed statistic (the selection of
+    awq_quantizer.py:57-61) for a CUDA [n,K] matrix of per-batch rows."""
+    assert feats.is_cuda and feats.dim() == 2
+    K = feats.shape[1]
+    imp = seq_sum_rows(feats)
+    colmul = torch.empty(K, dtype=torch.float32, device=feats.device)
+    mask = torch.empty(K, dtype=torch.uint8, device=feats.device)
+    with _on(feats.device):
+        rc = _lib.load().b200q_topk_colmul(imp.data_ptr(), K, n_protect, 2.0, colmul.data_ptr(),
+                                           mask.data_ptr(), _stream())
+    _lib.check(rc, "topk_colmul")
+    return mask
+
+
 def gptq_parity_layer(W: torch.Tensor, n_bit: int) -> torch.Tensor:
     assert W.is_cuda and W.dim() == 2
     W = W.contiguous()

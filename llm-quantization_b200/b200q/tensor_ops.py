@@ -30,7 +30,7 @@ def release_workspace() -> None:
 
 
 def hessian_accum(X: torch.Tensor, rows_per_sample: int, H: Optional[torch.Tensor] = None,
-                  return_norms: bool = False):
+                  return_norms: bool = False, normalize: bool = True):
     """H (+)= sum_i X_i^T X_i / (||X_i||_F + 1e-5)^2 over equal-length samples of the CUDA [T,K]
     matrix X (fp32/fp16/bf16).  Returns H (fp32 [K,K]) or (H, norms)."""
     assert X.is_cuda and X.dim() == 2
@@ -46,7 +46,7 @@ def hessian_accum(X: torch.Tensor, rows_per_sample: int, H: Optional[torch.Tenso
     with _on(X.device):
         work = _workspace(X.device, lib.b200q_hessian_workspace(T, K, n))
         rc = lib.b200q_hessian_accum(X.data_ptr(), n, rows_per_sample, K, dtype_code(X),
-                                     H.data_ptr(), int(accumulate),
+                                     int(normalize), H.data_ptr(), int(accumulate),
                                      None if norms is None else norms.data_ptr(), work.data_ptr(),
                                      _stream())
     _lib.check(rc, "hessian_accum")
@@ -113,6 +113,59 @@ def gptq_compensated(W: torch.Tensor, H: torch.Tensor, n_bit: int, group: int, b
     if perm is not None:
         Q = Q[:, torch.argsort(perm)]
     return Q.to(W.dtype)
+
+
+def gram_matrix(input_feat: Sequence, in_features: int, device) -> torch.Tensor:
+    """X^T X / (number of rows) over all calibration features of a layer, fp32 [K,K]: the matrix
+    in which the AWQ search measures output reconstruction error.  Feature lists follow the same
+    conventions as gptq_hessian (1-D entries are single rows)."""
+    device = torch.device(device)
+    K = in_features
+    if isinstance(input_feat, torch.Tensor):
+        X = input_feat.reshape(-1, K)
+    else:
+        X = torch.cat([f.reshape(-1, K) for f in input_feat])
+    X = X.to(device)
+    if X.dtype not in DTYPE_CODE:
+        X = X.float()
+    rows_total = X.shape[0]
+    # samples only matter for the fp16 pre-scaling here; use runs of up to 2048 rows
+    rows = 1
+    for cand in (2048, 1024, 512, 256, 128, 64, 32, 16, 8, 4, 2):
+        if rows_total % cand == 0:
+            rows = cand
+            break
+    if _dist.is_sharded():
+        n = rows_total // rows
+        lo, hi = _dist.shard_rows(n, _dist.world_size(), _dist.rank())
+        H = hessian_accum(X[lo * rows:hi * rows], rows, normalize=False) if hi > lo else \
+            torch.zeros((K, K), dtype=torch.float32, device=device)
+        _dist.allreduce_sum(H)
+    else:
+        H = hessian_accum(X, rows, normalize=False)
+    return hessian_finalize(H, 1.0 / rows_total, 0.0)
+
+
+def awq_search_losses(W: torch.Tensor, H: torch.Tensor, salient_mask: torch.Tensor, n_bit: int,
+                      group: int, candidates: Sequence[float]) -> torch.Tensor:
+    """fp32 [n_cand]: sum_rows dW_c H dW_c^T for every candidate scale factor, for the CUDA [N,K]
+    weight W (this rank's row shard under sharding; the caller all-reduces)."""
+    assert W.is_cuda and W.dim() == 2 and H.shape == (W.shape[1], W.shape[1])
+    import ctypes as C
+    W = W.contiguous()
+    N, K = W.shape
+    n_cand = len(candidates)
+    lib = _lib.load()
+    loss = torch.zeros(n_cand, dtype=torch.float32, device=W.device)
+    sf = (C.c_float * n_cand)(*[float(c) for c in candidates])
+    mask = salient_mask.to(device=W.device, dtype=torch.uint8).contiguous()
+    with _on(W.device):
+        work = _workspace(W.device, lib.b200q_awq_search_workspace(N, K, n_cand))
+        rc = lib.b200q_awq_search_loss(W.data_ptr(), N, K, group, n_bit, mask.data_ptr(), sf, n_cand,
+                                       H.contiguous().data_ptr(), dtype_code(W), work.data_ptr(),
+                                       loss.data_ptr(), _stream())
+    _lib.check(rc, "awq_search_loss")
+    return loss
 
 
 def gptq_hessian(input_feat: Sequence, in_features: int, device, perp_damp: float = 0.01,

@@ -438,6 +438,120 @@ group128_kernel(const T* __restrict__ W, T* __restrict__ out, GroupQuantArgs a) 
   }
 }
 
+// =================================================================================================
+// AWQ scale search, stage 1: dW_c = Q_c(W) - W for every candidate scale factor, as bf16
+// (ref: awq_quantizer.py:116-119 "for each scale factor, quantize and measure reconstruction error";
+//  Q_c is exactly awq_quantize_model_weight's arithmetic with scale_factor = sf_c, :70-81).
+// One read of W serves all candidates: a group stays in registers while the candidates are
+// quantised one after the other; candidate c's deltas go to D + c * rows_pad * K.
+// =================================================================================================
+struct CandParam {
+  float sf[32];
+  float sf_rcp[32];
+  int n;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+awq_delta128_kernel(const T* __restrict__ W, __nv_bfloat16* __restrict__ D,
+                    const uint8_t* __restrict__ salient, int64_t n_groups, int64_t K,
+                    int64_t cand_stride, float maxint, CandParam cp) {
+  constexpr int VEC = ST<T>::VEC;
+  constexpr int NV = 16 / VEC;
+  const int lane = threadIdx.x & 31;
+  const int l8 = lane & 7, sub = lane >> 3;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t groups_per_row = K / 128;
+  GroupQuantArgs a;
+  a.maxint = maxint;
+  for (int64_t base = warp * 4; base < n_groups; base += nwarps * 4) {
+    const int64_t g = base + sub;
+    const bool valid = g < n_groups;
+    const int64_t gg = valid ? g : n_groups - 1;
+    const T* wp = W + gg * 128 + l8 * VEC;
+    float w[16];
+    uint32_t smask = 0;     // bit e: element e of this lane sits on a salient column
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float t[VEC];
+      load_vec<T>(wp + i * 8 * VEC, t);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) w[i * VEC + j] = t[j];
+    }
+    const int64_t c0 = (gg % groups_per_row) * 128 + l8 * VEC;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j)
+        smask |= (salient[c0 + i * 8 * VEC + j] ? 1u : 0u) << (i * VEC + j);
+    for (int c = 0; c < cp.n; ++c) {
+      float x[16], cv[16], cr[16], code[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const bool s = (smask >> e) & 1u;
+        cv[e] = s ? cp.sf[c] : 1.f;
+        cr[e] = s ? cp.sf_rcp[c] : 1.f;
+        x[e] = ST<T>::rnd(w[e] * cv[e]);
+      }
+      float mx = x[0], mn = x[0];
+#pragma unroll
+      for (int e = 1; e < 16; ++e) { mx = fmaxf(mx, x[e]); mn = fminf(mn, x[e]); }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      }
+      float scale, zp;
+      // the search only ranks candidates: the (exact for |w| < 1e18) fast division is enough here
+      quantize_group16<T, false, B200Q_COLOP_MUL_DIV, false>(x, cv, cr, mx, mn, a, scale, zp, code);
+      if (valid) {
+        __nv_bfloat16* dp = D + c * cand_stride + g * 128 + l8 * VEC;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          float t[VEC];
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) t[j] = x[i * VEC + j] - w[i * VEC + j];
+          if constexpr (VEC == 8) {
+            store_vec<__nv_bfloat16>(dp + i * 64, t);
+          } else {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(t[0], t[1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(t[2], t[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(dp + i * 32) = pk;
+          }
+        }
+      }
+    }
+  }
+}
+
+int launch_awq_delta(const void* W, void* D, const uint8_t* salient, int64_t N, int64_t K,
+                     int64_t cand_stride, int n_bit, const float* sf_host, int n_cand, int dtype,
+                     cudaStream_t st) {
+  B200Q_REQUIRE(K % 128 == 0, "awq_search: in_features must be a multiple of 128 (group size)");
+  B200Q_REQUIRE(n_cand >= 1 && n_cand <= 32, "awq_search: 1..32 candidates");
+  B200Q_REQUIRE(aligned16(W) && aligned16(D), "awq_search: unaligned pointer");
+  CandParam cp;
+  cp.n = n_cand;
+  for (int i = 0; i < 32; ++i) {
+    cp.sf[i] = i < n_cand ? sf_host[i] : 1.f;
+    cp.sf_rcp[i] = 1.0f / cp.sf[i];
+  }
+  const int64_t n_groups = N * (K / 128);
+  const int64_t warps_needed = (n_groups + 3) / 4;
+  int64_t blocks = std::min<int64_t>((warps_needed + 7) / 8, (int64_t)kNumSMs * 8);
+  const float maxint = (float)((1 << n_bit) - 1);
+  B200Q_DISPATCH_DTYPE(dtype, T,
+                       (awq_delta128_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(
+                           static_cast<const T*>(W), static_cast<__nv_bfloat16*>(D), salient,
+                           n_groups, K, cand_stride, maxint, cp)));
+  count_launch();
+  return check_launch("awq_delta");
+}
+
 // any group length: one warp per group, two passes (the second re-reads through L2).
 template <typename T, bool SYM, int COLOP>
 __global__ void __launch_bounds__(256)

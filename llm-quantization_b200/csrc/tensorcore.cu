@@ -74,7 +74,8 @@ sample_stats_partial_kernel(const T* __restrict__ X, int64_t rows_per_sample, in
 // one block: norms[i] = sqrt(sum), alpha[i] = 1/(norm + 1e-5); global power-of-two factor
 // stats layout: [0, n) alpha_i * 2^s ; [n, 2n) norms ; [2n] = 2^-2s
 __global__ void sample_stats_finish_kernel(const float* __restrict__ partial, int chunks,
-                                           int n_samples, float* __restrict__ stats) {
+                                           int n_samples, float* __restrict__ stats,
+                                           int normalize) {
   __shared__ float s_big[256];
   float big = 0.f;
   for (int s = threadIdx.x; s < n_samples; s += blockDim.x) {
@@ -85,7 +86,7 @@ __global__ void sample_stats_finish_kernel(const float* __restrict__ partial, in
       amax = fmaxf(amax, partial[((int64_t)s * chunks + c) * 2 + 1]);
     }
     const float norm = (float)sqrt(sum);
-    const float alpha = 1.f / (norm + 1e-5f);            // gptq_quantizer.py:143
+    const float alpha = normalize ? 1.f / (norm + 1e-5f) : 1.f;   // gptq_quantizer.py:143
     stats[n_samples + s] = norm;
     stats[s] = alpha;
     big = fmaxf(big, alpha * amax);
@@ -401,6 +402,203 @@ static HessianWork hessian_layout(void* work, int64_t T, int64_t K, int n_sample
   return w;
 }
 
+// =================================================================================================
+// AWQ scale search, stage 2: loss_c = sum_rows dW_c H dW_c^T = <dW_c H, dW_c>
+// One tcgen05 GEMM over all candidates stacked along M:  P = D * Hb  (D [n_cand * rows_pad, K]
+// bf16, Hb = bf16(H) [K, K], symmetric so Hb[n, k] serves as the K-major B operand), with the
+// dot product <P, D> fused into the epilogue: the 128x256 fp32 tile leaves TMEM, is multiplied
+// with the matching bf16 tile of D and reduced to ONE float per CTA.  Per-candidate sums are
+// formed afterwards in a fixed order (deterministic).
+// Both operands are K-major: a TMA box is 64 k-elements (128 bytes) x 128 / 256 rows, i.e. rows of
+// one 128-byte swizzle row each; UMMA descriptors advance 32 bytes per K = 16 step inside the row.
+// =================================================================================================
+namespace ag {
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;     // 16 KiB
+constexpr int B_BYTES = BN * BK * 2;     // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int THREADS = 256;
+constexpr uint32_t TMEM_COLS = 256;
+constexpr int RASTER_M = 16;
+}  // namespace ag
+
+__global__ void __launch_bounds__(ag::THREADS, 1)
+awq_loss_gemm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_h,
+                     const __nv_bfloat16* __restrict__ D, float* __restrict__ tile_loss, int64_t Mtot,
+                     int64_t K, int tiles_n) {
+  using namespace ag;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* warp_sum = reinterpret_cast<float*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (int)((Mtot + BM - 1) / BM);
+  const int band = blockIdx.x / (RASTER_M * tiles_n);
+  const int within = blockIdx.x % (RASTER_M * tiles_n);
+  const int band_rows = min(RASTER_M, tiles_m - band * RASTER_M);
+  const int n_blk = within / band_rows;
+  const int m_blk = band * RASTER_M + within % band_rows;
+  const int num_kb = (int)((K + BK - 1) / BK);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_d);
+    tma_prefetch_desc(&tmap_h);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* a_dst = smem + stage * STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        tma_load_2d(a_dst, &tmap_d, &full_bar[stage], kb * BK, m_blk * BM);
+        tma_load_2d(a_dst + A_BYTES, &tmap_h, &full_bar[stage], kb * BK, n_blk * BN);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN, /*bf16=*/true, /*a_mn=*/false, /*b_mn=*/false);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t da = make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+          mma_f16_ss(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        mma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(tmem_full_bar);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after_sync();
+    float acc = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      tmem_ld_wait();
+      const int64_t col0 = (int64_t)n_blk * BN + c * 32;
+      if (row < Mtot && col0 < K) {
+        const __nv_bfloat16* dp = D + row * K + col0;
+        if (col0 + 32 <= K) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(dp + j);
+            float d[8];
+            unpack16<__nv_bfloat16>(raw, d);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc = fmaf(__uint_as_float(v[j + t]), d[t], acc);
+          }
+        } else {
+          for (int j = 0; j < 32 && col0 + j < K; ++j)
+            acc = fmaf(__uint_as_float(v[j]), __bfloat162float(dp[j]), acc);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) warp_sum[q] = acc;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x == 0)
+    tile_loss[(int64_t)m_blk * tiles_n + n_blk] = (warp_sum[0] + warp_sum[1]) + (warp_sum[2] + warp_sum[3]);
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                   int64_t n) {
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n;
+       i += (int64_t)gridDim.x * blockDim.x * 2) {
+    if (i + 1 < n) {
+      *reinterpret_cast<__nv_bfloat162*>(dst + i) = __floats2bfloat162_rn(src[i], src[i + 1]);
+    } else {
+      dst[i] = __float2bfloat16_rn(src[i]);
+    }
+  }
+}
+
+// loss[c] (+)= sum over the tile rows of candidate c, fixed order, fp64 accumulate
+__global__ void awq_loss_reduce_kernel(const float* __restrict__ tile_loss, int tiles_per_cand,
+                                       int n_cand, float* __restrict__ loss) {
+  const int c = blockIdx.x;
+  if (c >= n_cand) return;
+  __shared__ double sm[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < tiles_per_cand; i += blockDim.x)
+    s += (double)tile_loss[(int64_t)c * tiles_per_cand + i];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[c] += (float)sm[0];
+}
+
+static int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows,
+                          int box_cols) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return fail(B200Q_ECUDA, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200Q_ECUDA, "cuTensorMapEncodeTiled (bf16) failed");
+  return B200Q_OK;
+}
+
+struct AwqWork {
+  __nv_bfloat16* D;
+  __nv_bfloat16* Hb;
+  float* tile_loss;
+  int64_t rows_pad, bytes;
+  int tiles_n, tiles_per_cand;
+};
+
+static AwqWork awq_layout(void* work, int64_t N, int64_t K, int n_cand) {
+  auto align = [](int64_t x) { return (x + 255) / 256 * 256; };
+  AwqWork w;
+  w.rows_pad = (N + ag::BM - 1) / ag::BM * ag::BM;
+  w.tiles_n = (int)((K + ag::BN - 1) / ag::BN);
+  w.tiles_per_cand = (int)(w.rows_pad / ag::BM) * w.tiles_n;
+  uint8_t* base = static_cast<uint8_t*>(work);
+  int64_t off = 0;
+  w.D = reinterpret_cast<__nv_bfloat16*>(base + off); off += align(2 * (int64_t)n_cand * w.rows_pad * K);
+  w.Hb = reinterpret_cast<__nv_bfloat16*>(base + off); off += align(2 * K * K);
+  w.tile_loss = reinterpret_cast<float*>(base + off); off += align(4 * (int64_t)n_cand * w.tiles_per_cand);
+  w.bytes = off;
+  return w;
+}
+
 }  // namespace b200q
 
 using namespace b200q;
@@ -413,7 +611,8 @@ int64_t b200q_hessian_workspace(int64_t T, int64_t K, int n_samples) {
 }
 
 int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, int64_t K, int dtype,
-                        float* H, int accumulate, float* norms_out, void* work, void* stream) {
+                        int normalize, float* H, int accumulate, float* norms_out, void* work,
+                        void* stream) {
   B200Q_REQUIRE(X && H && work, "hessian_accum: null pointer");
   B200Q_REQUIRE(n_samples > 0 && rows_per_sample > 0 && K > 0, "hessian_accum: bad shape");
   B200Q_REQUIRE(K % 8 == 0, "hessian_accum: in_features must be a multiple of 8");
@@ -432,7 +631,8 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
       dim3 g1((unsigned)w.chunks, (unsigned)n_samples);
       sample_stats_partial_kernel<Tt><<<g1, 256, 0, st>>>(static_cast<const Tt*>(X),
                                                           rows_per_sample, K, w.partial_st);
-      sample_stats_finish_kernel<<<1, 256, 0, st>>>(w.partial_st, w.chunks, n_samples, w.stats);
+      sample_stats_finish_kernel<<<1, 256, 0, st>>>(w.partial_st, w.chunks, n_samples, w.stats,
+                                                    normalize);
       const int64_t total_vec = T * K / VEC;
       const int blocks = (int)std::min<int64_t>((total_vec + 255) / 256, (int64_t)kNumSMs * 16);
       prescale_kernel<Tt><<<blocks, 256, 0, st>>>(static_cast<const Tt*>(X), w.Xs, rows_per_sample,
@@ -493,6 +693,56 @@ int b200q_hessian_finalize(float* H, int64_t K, float scale, float damp, void* s
   hessian_finalize_kernel<<<blocks, 256, 0, st>>>(H, K, scale, damp);
   count_launch();
   return check_launch("hessian_finalize");
+}
+
+
+int64_t b200q_awq_search_workspace(int64_t N, int64_t K, int n_cand) {
+  if (N <= 0 || K <= 0 || n_cand <= 0) return 0;
+  return awq_layout(nullptr, N, K, n_cand).bytes;
+}
+
+int b200q_awq_search_loss(const void* W, int64_t N, int64_t K, int64_t group, int n_bit,
+                          const uint8_t* salient, const float* sf_host, int n_cand, const float* H,
+                          int dtype, void* work, float* loss, void* stream) {
+  B200Q_REQUIRE(W && salient && sf_host && H && work && loss, "awq_search_loss: null pointer");
+  B200Q_REQUIRE(N > 0 && K > 0, "awq_search_loss: bad shape");
+  if (group != 128) return fail(B200Q_EUNSUPPORTED, "awq_search_loss: group size must be 128");
+  B200Q_REQUIRE(K % 128 == 0, "awq_search_loss: in_features must be a multiple of 128");
+  B200Q_REQUIRE(aligned16(work), "awq_search_loss: unaligned workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AwqWork w = awq_layout(work, N, K, n_cand);
+  const int64_t Mtot = (int64_t)n_cand * w.rows_pad;
+  int rc;
+  {
+    KernelScope scope("awq_search_delta",
+                      (double)N * K * (elem_size(dtype) + 2.0 * n_cand), 0, st);
+    if (w.rows_pad != N)   // padding rows must be zero: they are read by the GEMM
+      cudaMemsetAsync(w.D, 0, 2 * Mtot * K, st);
+    rc = launch_awq_delta(W, w.D, salient, N, K, w.rows_pad * K, n_bit, sf_host, n_cand, dtype, st);
+    if (rc != B200Q_OK) return rc;
+    const int blocks = (int)std::min<int64_t>((K * K / 2 + 255) / 256, (int64_t)kNumSMs * 16);
+    f32_to_bf16_kernel<<<blocks, 256, 0, st>>>(H, w.Hb, K * K);
+    count_launch();
+  }
+  CUtensorMap tmap_d, tmap_h;
+  rc = make_tmap_bf16(&tmap_d, w.D, Mtot, K, ag::BM, ag::BK);
+  if (rc != B200Q_OK) return rc;
+  rc = make_tmap_bf16(&tmap_h, w.Hb, K, K, ag::BN, ag::BK);
+  if (rc != B200Q_OK) return rc;
+  cudaFuncSetAttribute(awq_loss_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       ag::SMEM_BYTES);
+  {
+    KernelScope scope("awq_search_gemm", 0, 2.0 * (double)n_cand * N * K * K, st);
+    const int tiles_m = (int)(Mtot / ag::BM);
+    awq_loss_gemm_kernel<<<(unsigned)(tiles_m * w.tiles_n), ag::THREADS, ag::SMEM_BYTES, st>>>(
+        tmap_d, tmap_h, w.D, w.tile_loss, Mtot, K, w.tiles_n);
+    count_launch();
+    rc = check_launch("awq_loss_gemm");
+    if (rc != B200Q_OK) return rc;
+  }
+  awq_loss_reduce_kernel<<<n_cand, 256, 0, st>>>(w.tile_loss, w.tiles_per_cand, n_cand, loss);
+  count_launch();
+  return check_launch("awq_loss_reduce");
 }
 
 }  // extern "C"
