@@ -115,6 +115,10 @@ int b200q_col_scale(const void* W, void* out, const float* s, int64_t N, int64_t
 int64_t b200q_act_stat_workspace(int64_t T, int64_t K); /* bytes of device scratch for meanabs */
 int b200q_act_meanabs(const void* X, int64_t T, int64_t K, int dtype, float* out, void* work,
                       void* stream);
+/* the same for a batch of n_samples equal-length samples stacked along the rows: out is
+ * [n_samples, K]; work needs n_samples * b200q_act_stat_workspace(rows_per_sample, K) bytes */
+int b200q_act_meanabs_batched(const void* X, int n_samples, int64_t rows_per_sample, int64_t K,
+                              int dtype, float* out, void* work, void* stream);
 int b200q_act_maxabs(const void* X, int64_t T, int64_t K, int dtype, float* out, int accumulate,
                      void* stream);
 /* out[k] = ((0 + V[0,k]) + V[1,k]) + ... sequential, each partial sum rounded to V's dtype: the

@@ -45,6 +45,9 @@ def _feat_matrix(feats, device) -> torch.Tensor:
 def _stat_rows(feats: List[torch.Tensor], device) -> torch.Tensor:
     """[n, K] matrix of per-batch mean|x| rows from a feature list whose entries are either such
     vectors already (1-D) or raw [tokens, K] activations (reduced by the act_meanabs kernel)."""
+    if isinstance(feats, torch.Tensor) and feats.dim() == 3:
+        # [n, tokens, K] batch of raw activations: one batched reduction
+        return _ops.act_meanabs_batched(_ops.to_device(feats)).to(feats.dtype)
     rows = []
     for f in feats:
         if f.dim() == 1:
@@ -111,28 +114,34 @@ def awq_search_scale_factor(
     from b200q import tensor_ops as _tops
     from b200q import dist as _dist
     candidates = torch.linspace(float(lo), float(hi), int(n_grid), dtype=torch.float64).tolist()
-    total = None
-    for name, module in model.named_modules():
-        if not isinstance(module, nn.Linear) or name not in input_feat:
-            continue
-        W = _ops.to_device(module.weight.data)
+    totals = []
+
+    def compute(name, _module, W):
         K = W.shape[1]
         feats = input_feat[name]
         # 2-D [tokens, K] features are raw activations: their per-batch mean|x| is the statistic
         # the quantizer ranks channels by (quantization_utils.py:231); 1-D features already are it
-        if isinstance(feats, torch.Tensor):
-            stat_rows = feats if feats.dim() == 2 else _stat_rows(list(feats), W.device)
+        if isinstance(feats, torch.Tensor) and feats.dim() == 2:
+            stat_rows = feats
         else:
             stat_rows = _stat_rows(feats, W.device)
         n_protect = max(1, int(K * protect_ratio))
         mask = _ops.salient_mask(_feat_matrix(stat_rows, W.device), n_protect)
         H = _tops.gram_matrix(feats, K, W.device)
         loss = _tops.awq_search_losses(W, H, mask, w_bit, q_group_size, candidates)
-        total = loss if total is None else total + loss
-    if total is None:
+        if totals:
+            totals[0] += loss
+        else:
+            totals.append(loss)
+        return None                       # the search leaves the model untouched
+
+    # host-resident weights are prefetched one layer ahead; nothing is written back
+    _pipeline.run_layers([(n, m) for n, m in model.named_modules()
+                          if isinstance(m, nn.Linear) and n in input_feat], compute)
+    if not totals:
         best = (lo + hi) / 2.0
     else:
-        _dist.allreduce_sum(total)
+        total = _dist.allreduce_sum(totals[0])
         best = candidates[int(torch.argmin(total).item())]
     print(f"  -> Using scale factor: {best:.3f}")
     return float(best)

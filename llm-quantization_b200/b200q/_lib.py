@@ -35,6 +35,7 @@ SIGNATURES = {
     "b200q_col_scale": (C.c_int, [c_vp, c_vp, c_fp, c_i64, c_i64, C.c_int, C.c_int, c_vp]),
     "b200q_act_stat_workspace": (c_i64, [c_i64, c_i64]),
     "b200q_act_meanabs": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_fp, c_vp, c_vp]),
+    "b200q_act_meanabs_batched": (C.c_int, [c_vp, C.c_int, c_i64, c_i64, C.c_int, c_fp, c_vp, c_vp]),
     "b200q_act_maxabs": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_fp, C.c_int, c_vp]),
     "b200q_seq_sum_rows": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_fp, c_vp]),
     "b200q_profile_enable": (None, [C.c_int]),

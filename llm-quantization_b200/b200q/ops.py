@@ -180,6 +180,21 @@ def act_meanabs(X: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def act_meanabs_batched(X: torch.Tensor) -> torch.Tensor:
+    """Per-sample mean|x| of a CUDA [n_samples, tokens, K] batch -> fp32 [n_samples, K]."""
+    assert X.is_cuda and X.dim() == 3
+    X = X.contiguous()
+    n, T, K = X.shape
+    lib = _lib.load()
+    out = torch.empty((n, K), dtype=torch.float32, device=X.device)
+    work = torch.empty(n * lib.b200q_act_stat_workspace(T, K), dtype=torch.uint8, device=X.device)
+    with _on(X.device):
+        rc = lib.b200q_act_meanabs_batched(X.data_ptr(), n, T, K, dtype_code(X), out.data_ptr(),
+                                           work.data_ptr(), _stream())
+    _lib.check(rc, "act_meanabs_batched")
+    return out
+
+
 def act_maxabs(X: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """max over tokens of |x| per channel; with `out` given, a running max into it."""
     assert X.is_cuda

@@ -708,6 +708,9 @@ act_abssum_partial_kernel(const T* __restrict__ X, int64_t Trows, int64_t K, int
   const int64_t col0 = ((int64_t)blockIdx.x * 32 + tx) * VEC;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = min(Trows, r0 + (int64_t)rows_per_block);
+  // blockIdx.z = sample of a batch of equal-length samples stacked along the rows
+  X += (int64_t)blockIdx.z * Trows * K;
+  partial += (int64_t)blockIdx.z * gridDim.y * K;
   float acc[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
@@ -750,10 +753,11 @@ __global__ void act_mean_finish_kernel(const float* __restrict__ partial, int ch
                                        float count, float* __restrict__ out) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
+  partial += (int64_t)blockIdx.y * chunks * K;     // blockIdx.y = sample
   float v = 0.f;
   for (int c = 0; c < chunks; ++c) v += partial[(int64_t)c * K + k];
   // torch: sum (rounded to the tensor dtype) then div_ by the row count
-  out[k] = ST<T>::rnd(__fdiv_rn(ST<T>::rnd(v), count));
+  out[(int64_t)blockIdx.y * K + k] = ST<T>::rnd(__fdiv_rn(ST<T>::rnd(v), count));
 }
 
 template <typename T>
@@ -988,31 +992,51 @@ int b200q_col_scale(const void* W, void* out, const float* s, int64_t N, int64_t
   return check_launch("col_scale");
 }
 
-int64_t b200q_act_stat_workspace(int64_t T, int64_t K) {
-  // one fp32 partial row per row chunk; chunks never exceed 148*8
-  (void)T;
-  return (int64_t)sizeof(float) * K * (kNumSMs * 8 + 1);
+static int act_chunks(int64_t T, int64_t K, int n_samples, int vec, int* rpb_out) {
+  const int64_t col_tiles = (K + 32 * vec - 1) / (32 * vec);
+  int rpb = pick_rows_per_block(T, col_tiles * n_samples);
+  *rpb_out = rpb;
+  return (int)((T + rpb - 1) / rpb);
 }
 
-int b200q_act_meanabs(const void* X, int64_t T, int64_t K, int dtype, float* out, void* work,
-                      void* stream) {
-  B200Q_REQUIRE(X && out && work && T > 0 && K > 0, "act_meanabs: bad argument");
+int64_t b200q_act_stat_workspace(int64_t T, int64_t K) {
+  // one fp32 partial row per (sample, row chunk): callers of the batched form multiply by n_samples
+  int rpb;
+  const int chunks = act_chunks(T, K, 1, 4, &rpb);
+  return (int64_t)sizeof(float) * K * (chunks + 1);
+}
+
+// out[s, k] = mean over the rows_per_sample rows of sample s of |X|; X is [n_samples *
+// rows_per_sample, K].  One launch pair for the whole batch.
+int b200q_act_meanabs_batched(const void* X, int n_samples, int64_t rows_per_sample, int64_t K,
+                              int dtype, float* out, void* work, void* stream) {
+  B200Q_REQUIRE(X && out && work && n_samples > 0 && rows_per_sample > 0 && K > 0,
+                "act_meanabs: bad argument");
+  B200Q_REQUIRE(n_samples <= 65535, "act_meanabs: too many samples");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  KernelScope scope("act_meanabs", (double)T * K * elem_size(dtype), 0, st);
+  const int64_t T = rows_per_sample;
+  KernelScope scope("act_meanabs", (double)n_samples * T * K * elem_size(dtype), 0, st);
   B200Q_DISPATCH_DTYPE(dtype, Tt, {
     constexpr int VEC = ST<Tt>::VEC;
     B200Q_REQUIRE(aligned16(X) && K % VEC == 0, "act_meanabs: K must be a multiple of 16 bytes");
     const int64_t col_tiles = (K + 32 * VEC - 1) / (32 * VEC);
-    const int rpb = pick_rows_per_block(T, col_tiles);
-    const int chunks = (int)((T + rpb - 1) / rpb);
-    dim3 grid((unsigned)col_tiles, (unsigned)chunks);
+    int rpb;
+    // chunk count from the single-sample rule so that the workspace formula holds per sample
+    const int chunks = act_chunks(T, K, 1, 4, &rpb);
+    dim3 grid((unsigned)col_tiles, (unsigned)chunks, (unsigned)n_samples);
     act_abssum_partial_kernel<Tt><<<grid, 256, 0, st>>>(static_cast<const Tt*>(X), T, K, rpb,
                                                         static_cast<float*>(work));
-    act_mean_finish_kernel<Tt><<<(unsigned)((K + 255) / 256), 256, 0, st>>>(
-        static_cast<const float*>(work), chunks, K, (float)T, out);
+    dim3 g2((unsigned)((K + 255) / 256), (unsigned)n_samples);
+    act_mean_finish_kernel<Tt><<<g2, 256, 0, st>>>(static_cast<const float*>(work), chunks, K,
+                                                   (float)T, out);
   });
   count_launch(2);
   return check_launch("act_meanabs");
+}
+
+int b200q_act_meanabs(const void* X, int64_t T, int64_t K, int dtype, float* out, void* work,
+                      void* stream) {
+  return b200q_act_meanabs_batched(X, 1, T, K, dtype, out, work, stream);
 }
 
 int b200q_act_maxabs(const void* X, int64_t T, int64_t K, int dtype, float* out, int accumulate,

@@ -42,3 +42,44 @@ if "hessian" in which:
         del X
         T.release_workspace()
         torch.cuda.empty_cache()
+
+if "inverse" in which:
+    for K in (4096, 11008):
+        X = torch.randn(8192, K, device="cuda", dtype=torch.bfloat16)
+        H = T.hessian_finalize(T.hessian_accum(X, 2048), 1.0 / 4, 0.01)
+        del X
+        for name, kw in (("inverse", dict(want_inverse=True, want_upper=False)),
+                         ("upper_factor", dict(want_inverse=False, want_upper=True))):
+            q = timed(["spd_inverse"], lambda: T.spd_inverse(H, ridge=1e-6, **kw), reps=2)["spd_inverse"]
+            ms = q["ms"] / q["launches"]
+            print(json.dumps({"stage": name, "K": K, "ms": round(ms, 2),
+                              "tflops_fp32": round(q["flops"] / q["launches"] / (ms * 1e-3) / 1e12, 1)}))
+        T.release_workspace(); torch.cuda.empty_cache()
+
+if "search" in which:
+    for N, K in ((4096, 4096), (11008, 4096), (4096, 11008)):
+        W = torch.randn(N, K, device="cuda") * 0.02
+        X = torch.randn(4096, K, device="cuda", dtype=torch.bfloat16)
+        H = T.hessian_finalize(T.hessian_accum(X, 2048, normalize=False), 1.0 / 4096, 0.0)
+        mask = torch.zeros(K, dtype=torch.uint8, device="cuda"); mask[:: 100] = 1
+        cands = torch.linspace(1, 2, 20).tolist()
+        q = timed(["awq_search_delta", "awq_search_gemm"],
+                  lambda: T.awq_search_losses(W, H, mask, 4, 128, cands), reps=2)
+        g = q["awq_search_gemm"]; d = q["awq_search_delta"]
+        ms = g["ms"] / g["launches"]
+        print(json.dumps({"stage": "awq_search", "N": N, "K": K, "gemm_ms": round(ms, 3),
+                          "tflops": round(g["flops"] / g["launches"] / (ms * 1e-3) / 1e12, 1),
+                          "frac_of_bf16_peak": round(g["flops"] / g["launches"] / (ms * 1e-3) / 1e12 / PEAK, 3),
+                          "delta_ms": round(d["ms"] / d["launches"], 3),
+                          "delta_gbs": round(d["bytes"] / d["ms"] / 1e6, 0)}))
+        T.release_workspace(); torch.cuda.empty_cache()
+
+if "compensated" in which:
+    for N, K in ((4096, 4096),):
+        W = torch.randn(N, K, device="cuda") * 0.02
+        X = torch.randn(8192, K, device="cuda", dtype=torch.bfloat16)
+        H = T.hessian_finalize(T.hessian_accum(X, 2048), 1.0 / 4, 0.01)
+        q = timed(["gptq_compensated", "spd_inverse"], lambda: T.gptq_compensated(W, H, 4, 128), reps=2)
+        g = q["gptq_compensated"]
+        print(json.dumps({"stage": "gptq_compensated", "N": N, "K": K, "ms": round(g["ms"] / g["launches"], 2),
+                          "upper_factor_ms": round(q["spd_inverse"]["ms"] / q["spd_inverse"]["launches"], 2)}))
