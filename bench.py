@@ -269,6 +269,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: progress text of the entry points (the reference's
+    # functions print, e.g. "Searching for optimal scale factor...") goes to stderr
+    out = sys.stdout
+    sys.stdout = sys.stderr
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -305,7 +309,7 @@ def main():
             "data": "synthetic", "config": {"workload": workload}, "cpu_baseline": best,
             "e2e": {"value": best["value"], "unit": "rows/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+            "gpu_launches": 0}), file=out, flush=True)
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU path exists)"
@@ -498,7 +502,7 @@ def main():
         "stages": stages, "kernel_ms_per_step": kall["ms"] / args.steps,
         "result": result if isinstance(result, float) else None,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
     if world > 1:
         td.destroy_process_group()
 
