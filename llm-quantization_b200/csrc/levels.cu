@@ -128,6 +128,7 @@ struct PotConsts {
   int emax_idx;     // E_max_idx = 2^(b-1) - 1
   float tiny;       // finfo(dtype).tiny
   float ratio_min;  // 1e-10 in the tensor's dtype
+  float bmin, bmax; // smallest / largest positive grid multiplier (for the fast-path range check)
 };
 
 // E = clamp(round(log2(clamp(|w| / s, 1e-10))), 0, E_max_idx)      pot_apot_quantizer.py:87-88
@@ -161,8 +162,23 @@ pot128_f32_kernel(const float* __restrict__ w, float* __restrict__ out, uint8_t*
                   float* __restrict__ best_scale_out, int32_t* __restrict__ best_idx_out,
                   int64_t n_groups, PotConsts c, GridParam grid, int n_grid) {
   __shared__ uint32_t thr[128];
+  // Fast path table, indexed by the BIASED exponent of the ratio r = |w| / s:
+  //   lut[e].x = first bit pattern in that binade whose rne(log2f) rounds up (0xffffffff: never)
+  //   lut[e].y = bit pattern of 2^E_low, the level magnitude multiplier when it does not
+  // so that  2^E = as_float(lut.y + (bits(r) >= lut.x ? 1 << 23 : 0)).  Entry 0 (r == 0, i.e.
+  // w == 0: sign(0) = 0 makes w_q = 0) holds multiplier 0.
+  __shared__ uint2 lut[256];
   for (int i = threadIdx.x; i <= c.emax_idx; i += blockDim.x)
     thr[i] = (i < c.emax_idx) ? c_round_thr[i + 127] : 0xffffffffu;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    const int e = i - 127;
+    uint2 t;
+    if (i == 0) t = make_uint2(0xffffffffu, 0u);
+    else if (e < 0) t = make_uint2(0xffffffffu, 0x3f800000u);
+    else if (e >= c.emax_idx) t = make_uint2(0xffffffffu, (uint32_t)(c.emax_idx + 127) << 23);
+    else t = make_uint2(c_round_thr[e + 127], (uint32_t)(e + 127) << 23);
+    lut[i] = t;
+  }
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -175,17 +191,52 @@ pot128_f32_kernel(const float* __restrict__ w, float* __restrict__ out, uint8_t*
 #pragma unroll
   for (int v = 0; v < 16; ++v) x[v] = wp[v * 8];
 
-  float amax = 0.f;
+  float amax = 0.f, amin_nz = INFINITY;
 #pragma unroll
-  for (int v = 0; v < 16; ++v) amax = fmaxf(amax, fabsf(x[v]));
+  for (int v = 0; v < 16; ++v) {
+    const float a = fabsf(x[v]);
+    amax = fmaxf(amax, a);
+    amin_nz = fminf(amin_nz, a == 0.f ? INFINITY : a);
+  }
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  for (int o = 4; o > 0; o >>= 1) {
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    amin_nz = fminf(amin_nz, __shfl_xor_sync(0xffffffffu, amin_nz, o));
+  }
   float s0;
   pot_base_scale(amax, c, s0);
 
   float best_err = INFINITY;
   float best_scale = s0;
   int best_idx = -1;
+  // The LUT path needs the ratio to be a normal float computed by the exact reused-divisor
+  // division: every non-zero |w| and every candidate scale inside [1e-18, 1e18] (any sane weight
+  // group; NaN fails the comparisons).  Other groups take the general path below.
+  const bool fast = (amax < 1e18f) && (amin_nz > 1e-18f) && (s0 * c.bmin > 1e-18f) &&
+                    (s0 * c.bmax < 1e18f) && (c.bmin > 0.f);
+  if (fast) {
+    for (int ci = 0; ci < n_grid; ++ci) {
+      const float s = fmaxf(s0 * grid.b[ci], c.tiny);                     // :81-82
+      const Divisor sd(s);
+      float acc[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] = 0.f;
+#pragma unroll
+      for (int v = 0; v < 16; ++v) {
+        const float aw = fabsf(x[v]);
+        const uint32_t rb = __float_as_uint(sd.div_core(aw));             // r = |w| / s_b   :87
+        const uint2 t = lut[rb >> 23];
+        const float p2 = __uint_as_float(t.y + (rb >= t.x ? 0x00800000u : 0u));   // 2^E     :88
+        const float d = aw - s * p2;         // |w - s*sign(w)*2^E| = | |w| - s*2^E |       :91,94
+        acc[v & 3] += d * d;
+      }
+      float p = ((acc[0] + acc[1]) + acc[2]) + acc[3];
+      float err = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) err += __shfl_sync(0xffffffffu, p, q, 8);
+      if (err < best_err) { best_err = err; best_scale = s; best_idx = ci; }   // :97-99
+    }
+  } else
   for (int ci = 0; ci < n_grid; ++ci) {
     // s_b = clamp(s_0 * b, tiny)                                       :81-82
     const float s = fmaxf(s0 * grid.b[ci], c.tiny);
@@ -432,6 +483,12 @@ int b200q_pot_quant(const void* w, void* out, uint8_t* exps, float* best_scale, 
   c.emax_idx = (1 << (n_bit - 1)) - 1;
   c.tiny = 1.17549435e-38f;
   c.ratio_min = 1e-10f;
+  c.bmin = grid_host[0];
+  c.bmax = grid_host[0];
+  for (int i = 1; i < n_grid; ++i) {
+    c.bmin = fminf(c.bmin, grid_host[i]);
+    c.bmax = fmaxf(c.bmax, grid_host[i]);
+  }
   GridParam gp;
   for (int i = 0; i < 256; ++i) gp.b[i] = i < n_grid ? grid_host[i] : 0.f;
   const float* wf = static_cast<const float*>(w);

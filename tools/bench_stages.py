@@ -83,3 +83,18 @@ if "compensated" in which:
         g = q["gptq_compensated"]
         print(json.dumps({"stage": "gptq_compensated", "N": N, "K": K, "ms": round(g["ms"] / g["launches"], 2),
                           "upper_factor_ms": round(q["spd_inverse"]["ms"] / q["spd_inverse"]["launches"], 2)}))
+
+if "levels" in which:
+    from b200q import ops
+    sys.path.insert(0, str(REPO / "llm-quantization_b200"))
+    from pot_apot_quantizer import _apot_signed_levels
+    W = torch.randn(4096, 4096, device="cuda") * 0.02
+    grp = W.view(-1, 128)
+    for name, fn, evals in (
+            ("pot_quant", lambda: ops.pot_quant(grp, 4, torch.arange(0.01, 2.01, 0.01)), 200),
+            ("apot_quant", lambda: ops.apot_quant(grp, _apot_signed_levels(4, 2), torch.arange(0.01, 2.01, 0.1)), 20)):
+        q = timed([name], fn, reps=3)[name]
+        ms = q["ms"] / q["launches"]
+        print(json.dumps({"stage": name, "shape": "4096x4096 f32 g128", "ms": round(ms, 3),
+                          "gbs_algorithmic": round(q["bytes"] / q["launches"] / ms / 1e6, 1),
+                          "T_candidate_evals_per_s": round(W.numel() * evals / (ms * 1e-3) / 1e12, 3)}))
