@@ -22,7 +22,7 @@
 namespace b200q {
 
 namespace la {
-constexpr int NB = 128;
+constexpr int NB = 64;    // diagonal block: the one-CTA factor+inverse kernel is on the critical path K/NB times
 constexpr int BM = 128, BN = 128, BK = 16;
 }  // namespace la
 
@@ -36,11 +36,18 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 sgemm_kernel(int M, int N, int Kd, float alpha, const float* __restrict__ A, int64_t lda,
              const float* __restrict__ B, int64_t ldb, float beta, float* __restrict__ C,
-             int64_t ldc, int tri) {
+             int64_t ldc, int tri, int64_t batch_stride) {
   using namespace la;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   if (tri == 1 && n0 > m0 + BM - 1) return;
+  // blockIdx.z = problem of a batch whose operands all advance by the same stride (the diagonal
+  // block pairs of the divide-and-conquer triangular inverse)
+  A += (int64_t)blockIdx.z * batch_stride;
+  B += (int64_t)blockIdx.z * batch_stride;
+  C += (int64_t)blockIdx.z * batch_stride;
   const int k_first = (tri == 2) ? (max(m0, n0) / BK) : (tri == 3 ? n0 / BK : 0);
+  // tri == 4: A lower triangular (A[m,k] = 0 for k > m): k stops after this tile's last row
+  if (tri == 4) Kd = min(Kd, m0 + BM);
   __shared__ float As[2][BK][BM + 4];
   __shared__ float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x;
@@ -131,62 +138,124 @@ sgemm_kernel(int M, int N, int Kd, float alpha, const float* __restrict__ A, int
 
 template <bool TA, bool TB>
 static void sgemm(cudaStream_t st, int M, int N, int Kd, float alpha, const float* A, int64_t lda,
-                  const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int tri = 0) {
-  if (M <= 0 || N <= 0) return;
-  dim3 grid((N + la::BN - 1) / la::BN, (M + la::BM - 1) / la::BM);
-  sgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(M, N, Kd, alpha, A, lda, B, ldb, beta, C, ldc, tri);
+                  const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int tri = 0,
+                  int batch = 1, int64_t batch_stride = 0) {
+  if (M <= 0 || N <= 0 || batch <= 0) return;
+  dim3 grid((N + la::BN - 1) / la::BN, (M + la::BM - 1) / la::BM, batch);
+  sgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(M, N, Kd, alpha, A, lda, B, ldb, beta, C, ldc, tri,
+                                             batch_stride);
   count_launch();
 }
 
-// One CTA: Cholesky of the nb x nb diagonal block at A (lower, in place; the strict upper part of
-// the block is zeroed) and its inverse into Linv (nb x nb, ld = NB, lower).  info = first
-// non-positive pivot (1-based, offset by j0), left untouched on success.
-__global__ void __launch_bounds__(256)
+// One CTA of 128 threads: Cholesky of the nb x nb (nb <= 128) diagonal block at A (lower, in place;
+// the strict upper part of the block is zeroed) and its inverse into Linv (dense nb x nb copy,
+// ld = NB) and Linv_big (ld = lda).  info = first non-positive pivot (1-based, offset by j0).
+//
+// Left-looking: in step k the threads of row r form A[r][k] - sum_{j<k} L[r][j] L[k][j] from
+// their own row and the pivot row (a broadcast), and accumulate the pivot's own sum in the same
+// loop, so every thread knows sqrt(pivot) without an exchange: two barriers per column and no
+// rank-1 sweeps.  The inverse is a forward substitution per column.  This kernel sits on the
+// critical path K/128 times, so its latency decides the factorisation time for K <= ~8K.
+__global__ void __launch_bounds__(512)
 potrf_inv_diag_kernel(float* __restrict__ A, int64_t lda, int nb, float* __restrict__ Linv,
-                      int* __restrict__ info, int j0) {
+                      float* __restrict__ Linv_big, int* __restrict__ info, int j0) {
+  // FOUR threads per row (512 threads, 16 warps = 4 per scheduler): ncu on the one-thread-per-row
+  // version showed 19 % issue utilisation, every instruction waiting ~5 cycles on the previous one
+  // with a single warp per scheduler.  The 4 lanes of a row take j = q, q+4, ... and combine with
+  // two shuffles.  LD = 132 (= 4 mod 32) makes (row, q) -> bank 4*row + q conflict free.
   extern __shared__ float sm[];
-  float* L = sm;                          // [NB][NB+1]
-  float* X = sm + la::NB * (la::NB + 1);  // [NB][NB+1]
+  constexpr int LD = la::NB + 4;
+  float* L = sm;                 // [NB][LD]
+  float* X = sm + la::NB * LD;   // [NB][LD]
   const int tid = threadIdx.x;
-  constexpr int LD = la::NB + 1;
-  for (int i = tid; i < nb * nb; i += blockDim.x) {
-    const int r = i / nb, c = i % nb;
-    L[r * LD + c] = (c <= r) ? A[(int64_t)r * lda + c] : 0.f;
+  for (int i = tid; i < la::NB * la::NB; i += blockDim.x) {
+    const int r = i / la::NB, c = i % la::NB;
+    L[r * LD + c] = (r < nb && c <= r) ? A[(int64_t)r * lda + c] : (r == c ? 1.f : 0.f);
+    X[r * LD + c] = 0.f;
   }
   __syncthreads();
+  const int r = tid >> 2, q = tid & 3;
   for (int k = 0; k < nb; ++k) {
-    const float d = L[k * LD + k];
-    if (!(d > 0.f)) {
-      if (tid == 0 && info != nullptr) atomicCAS(info, 0, j0 + k + 1);
+    float t = 0.f, d = 0.f;
+    const float* lr = L + r * LD;
+    const float* lk = L + k * LD;
+    // batches of 8 predicated loads first, FMAs after: the trip count is short (<= 32) and a
+    // rolled load->FMA loop would pay the full shared-memory latency on every iteration
+    float t1 = 0.f, d1 = 0.f;
+    for (int base = q; base < k; base += 32) {
+      float a[8], p[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = base + 4 * u;
+        const bool ok = j < k;
+        a[u] = ok ? lr[j] : 0.f;
+        p[u] = ok ? lk[j] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) {
+        t = fmaf(-a[u], p[u], t);
+        t1 = fmaf(-a[u + 1], p[u + 1], t1);
+        d = fmaf(-p[u], p[u], d);
+        d1 = fmaf(-p[u + 1], p[u + 1], d1);
+      }
     }
+    t += t1;
+    d += d1;
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    t += lr[k];                            // A[r][k] - sum_j L[r][j] L[k][j]
+    d += lk[k];                            // A[k][k] - sum_j L[k][j]^2
     const float piv = sqrtf(fmaxf(d, 1e-30f));
-    __syncthreads();
-    // scale column k
-    for (int r = k + tid; r < nb; r += blockDim.x)
-      L[r * LD + k] = (r == k) ? piv : L[r * LD + k] / piv;
-    __syncthreads();
-    // rank-1 update of the trailing lower triangle
-    const int rem = nb - k - 1;
-    for (int i = tid; i < rem * rem; i += blockDim.x) {
-      const int r = k + 1 + i / rem, c = k + 1 + i % rem;
-      if (c <= r) L[r * LD + c] = fmaf(-L[r * LD + k], L[c * LD + k], L[r * LD + c]);
+    if (tid == 0 && !(d > 0.f) && info != nullptr) atomicCAS(info, 0, j0 + k + 1);
+    __syncthreads();                       // everyone has read column k of A / row k of L
+    if (q == 0) {
+      if (r == k) L[r * LD + k] = piv;
+      else if (r > k) L[r * LD + k] = t / piv;
     }
     __syncthreads();
   }
-  // inverse by forward substitution, one column per thread: L x = e_c
-  for (int c = tid; c < nb; c += blockDim.x) {
-    for (int r = 0; r < nb; ++r) {
-      if (r < c) { X[r * LD + c] = 0.f; continue; }
-      float s = (r == c) ? 1.f : 0.f;
-      for (int k = c; k < r; ++k) s = fmaf(-L[r * LD + k], X[k * LD + c], s);
-      X[r * LD + c] = s / L[r * LD + r];
+  // inverse by forward substitution: four threads per column c solve L x = e_c
+  const int c = tid >> 2;
+  // the columns of one warp have different trip counts: synchronise the 4-lane team only
+  const unsigned team = 0xFu << ((tid & 31) & ~3);
+  if (c < nb) {
+    for (int row = c; row < nb; ++row) {
+      float s = 0.f;
+      const float* lrow = L + row * LD;
+      float s1 = 0.f;
+      for (int base = c + q; base < row; base += 32) {
+        float a[8], x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k = base + 4 * u;
+          const bool ok = k < row;
+          a[u] = ok ? lrow[k] : 0.f;
+          x[u] = ok ? X[k * LD + c] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+          s = fmaf(-a[u], x[u], s);
+          s1 = fmaf(-a[u + 1], x[u + 1], s1);
+        }
+      }
+      s += s1;
+      s += __shfl_xor_sync(team, s, 1);
+      s += __shfl_xor_sync(team, s, 2);
+      if (row == c) s += 1.f;
+      if (q == 0) X[row * LD + c] = s / lrow[row];
+      __syncwarp(team);
     }
   }
   __syncthreads();
   for (int i = tid; i < nb * nb; i += blockDim.x) {
-    const int r = i / nb, c = i % nb;
-    A[(int64_t)r * lda + c] = L[r * LD + c];
-    Linv[r * la::NB + c] = X[r * LD + c];
+    const int rr = i / nb, cc = i % nb;
+    const float l = (cc <= rr) ? L[rr * LD + cc] : 0.f;
+    const float x = (cc <= rr) ? X[rr * LD + cc] : 0.f;
+    A[(int64_t)rr * lda + cc] = l;
+    Linv[rr * la::NB + cc] = x;
+    if (Linv_big != nullptr) Linv_big[(int64_t)rr * lda + cc] = x;
   }
 }
 
@@ -213,7 +282,7 @@ struct LinalgWork {
   float* A;      // [K,K] working copy -> L (lower)
   float* Linv;   // [K,K] -> L^-1 (lower)
   float* Dinv;   // [NB,NB] inverse of the current diagonal block
-  float* T;      // [NB,K] row-block temporary
+  float* T;      // [K,K] scratch for the block products of the triangular inverse
   int64_t bytes;
 };
 
@@ -225,7 +294,7 @@ static LinalgWork linalg_layout(void* work, int64_t K) {
   w.A = reinterpret_cast<float*>(base + off); off += align(4 * K * K);
   w.Linv = reinterpret_cast<float*>(base + off); off += align(4 * K * K);
   w.Dinv = reinterpret_cast<float*>(base + off); off += align(4 * la::NB * la::NB);
-  w.T = reinterpret_cast<float*>(base + off); off += align(4 * la::NB * K);
+  w.T = reinterpret_cast<float*>(base + off); off += align(4 * K * K);
   w.bytes = off;
   return w;
 }
@@ -233,38 +302,60 @@ static LinalgWork linalg_layout(void* work, int64_t K) {
 // A (K x K, lower part valid) -> L in place (lower), Linv = L^-1 (lower, upper part zero).
 static int cholesky_and_inverse(cudaStream_t st, const LinalgWork& w, int64_t K, int* info) {
   using namespace la;
-  const int diag_smem = 2 * NB * (NB + 1) * (int)sizeof(float);
+  const int diag_smem = 2 * NB * (NB + 4) * (int)sizeof(float);
   cudaFuncSetAttribute(potrf_inv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem);
   cudaMemsetAsync(w.Linv, 0, sizeof(float) * K * K, st);
-  for (int64_t j = 0; j < K; j += NB) {
-    const int nb = (int)std::min<int64_t>(NB, K - j);
-    float* Ajj = w.A + j * K + j;
-    potrf_inv_diag_kernel<<<1, 256, diag_smem, st>>>(Ajj, K, nb, w.Dinv, info, (int)j);
-    count_launch();
-    // diagonal block of L^-1
-    copy_block_kernel<<<16, 256, 0, st>>>(w.Dinv, NB, w.Linv + j * K + j, K, nb, nb);
-    count_launch();
-    const int rem = (int)(K - j - nb);
-    if (rem > 0) {
-      float* A21 = w.A + (j + nb) * K + j;
-      // L21 = A21 * L11^-T   -> into T (rem x nb), then back
-      sgemm<false, true>(st, rem, nb, nb, 1.f, A21, K, w.Dinv, NB, 0.f, w.T, NB);
-      // reuse: copy T back over A21 (row-block temporaries are at most NB wide, so T is [rem, NB])
-      copy_block_kernel<<<(unsigned)std::min<int64_t>(1024, ((int64_t)rem * nb + 255) / 256), 256, 0,
-                          st>>>(w.T, NB, A21, K, rem, nb);
+  {
+    KernelScope scope("inv_potrf", 0, (double)K * K * K / 3.0, st);
+    for (int64_t j = 0; j < K; j += NB) {
+      const int nb = (int)std::min<int64_t>(NB, K - j);
+      float* Ajj = w.A + j * K + j;
+      // factor the diagonal block; its inverse goes to Dinv (dense copy for the panel GEMM) and
+      // straight into the diagonal block of L^-1
+      {
+        KernelScope diag_scope("inv_diag", 0, 0, st);
+        potrf_inv_diag_kernel<<<1, 4 * NB, diag_smem, st>>>(Ajj, K, nb, w.Dinv, w.Linv + j * K + j, info,
+                                                         (int)j);
+      }
       count_launch();
-      // A22 -= L21 L21^T (lower tiles)
-      float* A22 = w.A + (j + nb) * K + (j + nb);
-      sgemm<false, true>(st, rem, rem, nb, -1.f, A21, K, A21, K, 1.f, A22, K, /*tri=*/1);
+      const int rem = (int)(K - j - nb);
+      if (rem > 0) {
+        float* A21 = w.A + (j + nb) * K + j;
+        // L21 = A21 * L11^-T, in place: the panel is one column tile wide (nb <= BN), so each CTA
+        // reads exactly the rows it later overwrites
+        sgemm<false, true>(st, rem, nb, nb, 1.f, A21, K, w.Dinv, NB, 0.f, A21, K);
+        // A22 -= L21 L21^T (lower tiles)
+        float* A22 = w.A + (j + nb) * K + (j + nb);
+        sgemm<false, true>(st, rem, rem, nb, -1.f, A21, K, A21, K, 1.f, A22, K, /*tri=*/1);
+      }
     }
   }
-  // L^-1 below the diagonal, block row i:  Linv[i, 0:i] = -Linv[i,i] * (L[i, 0:i] * Linv[0:i, 0:i])
-  for (int64_t i = NB; i < K; i += NB) {
-    const int nb = (int)std::min<int64_t>(NB, K - i);
-    const float* Li = w.A + i * K;                 // L[i-block, 0:i]
-    sgemm<false, false>(st, nb, (int)i, (int)i, 1.f, Li, K, w.Linv, K, 0.f, w.T, K, /*tri=*/3);
-    sgemm<false, false>(st, nb, (int)i, nb, -1.f, w.Linv + i * K + i, K, w.T, K, 0.f,
-                        w.Linv + i * K, K);
+  // L^-1 by divide and conquer over the block diagonal: with M11, M22 the inverses of two adjacent
+  // s x s diagonal blocks and L21 the block below the first,  M21 = -M22 * (L21 * M11).
+  // Level s handles all K/(2s) pairs at once (batched launch, operands advance by 2s*(K+1)); the
+  // last pair of a level may be ragged.  Every level is two GEMMs with full 2-D parallelism, where
+  // a row- or column-sweep exposes only K/128 CTAs.
+  {
+    KernelScope scope("inv_trtri", 0, (double)K * K * K / 3.0, st);
+    for (int64_t s = NB; s < K; s *= 2) {
+      const int64_t full = K / (2 * s);                       // pairs with two complete blocks
+      const int64_t stride = 2 * s * (K + 1);
+      auto level = [&](int64_t a, int64_t s2, int batch) {
+        const float* L21 = w.A + (a + s) * K + a;
+        float* S21 = w.T + (a + s) * K + a;
+        float* M21 = w.Linv + (a + s) * K + a;
+        // S21 = L21 * M11          (M11 lower triangular: k starts at the column tile)
+        sgemm<false, false>(st, (int)s2, (int)s, (int)s, 1.f, L21, K, w.Linv + a * K + a, K, 0.f, S21,
+                            K, /*tri=*/3, batch, stride);
+        // M21 = -M22 * S21         (M22 lower triangular: k stops at the row tile)
+        sgemm<false, false>(st, (int)s2, (int)s, (int)s2, -1.f, w.Linv + (a + s) * K + (a + s), K, S21,
+                            K, 0.f, M21, K, /*tri=*/4, batch, stride);
+      };
+      if (full > 0) level(0, s, (int)full);
+      const int64_t a = full * 2 * s;                         // ragged tail: second block is short
+      const int64_t s2 = K - a - s;
+      if (s2 > 0) level(a, s2, 1);
+    }
   }
   return check_launch("cholesky_and_inverse");
 }

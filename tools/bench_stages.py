@@ -50,9 +50,12 @@ if "inverse" in which:
         del X
         for name, kw in (("inverse", dict(want_inverse=True, want_upper=False)),
                          ("upper_factor", dict(want_inverse=False, want_upper=True))):
-            q = timed(["spd_inverse"], lambda: T.spd_inverse(H, ridge=1e-6, **kw), reps=2)["spd_inverse"]
+            qq = timed(["spd_inverse", "inv_potrf", "inv_trtri"], lambda: T.spd_inverse(H, ridge=1e-6, **kw), reps=2)
+            q = qq["spd_inverse"]
             ms = q["ms"] / q["launches"]
             print(json.dumps({"stage": name, "K": K, "ms": round(ms, 2),
+                              "potrf_ms": round(qq["inv_potrf"]["ms"] / qq["inv_potrf"]["launches"], 2),
+                              "trtri_ms": round(qq["inv_trtri"]["ms"] / qq["inv_trtri"]["launches"], 2),
                               "tflops_fp32": round(q["flops"] / q["launches"] / (ms * 1e-3) / 1e12, 1)}))
         T.release_workspace(); torch.cuda.empty_cache()
 
