@@ -72,6 +72,10 @@ int b200q_selftest_div(int64_t n_quotients, uint64_t seed, int64_t* mismatches, 
  * ref: pot_apot_quantizer.py:66,88,105 */
 uint32_t b200q_log2_round_threshold_bits(int e);  /* e in [-127,127] */
 uint32_t b200q_log2_floor_threshold_bits(int e);  /* e in [-149,127] */
+/* the same for fp16 / bf16 tensors (dtype = B200Q_F16 / B200Q_BF16): torch rounds log2's result to
+ * the tensor's type first, and the argument is a 16-bit value; 0x7f800000 = never reached */
+uint32_t b200q_log2_round_threshold_bits_dt(int e, int dtype);
+uint32_t b200q_log2_floor_threshold_bits_dt(int e, int dtype);
 
 /* ---- column statistics -------------------------------------------------------------
  * colmax[k] = max_i |W[i,k]|, as fp32.   ref: gptq_quantizer.py:182 (per column over

@@ -26,6 +26,8 @@ SIGNATURES = {
     "b200q_launch_count": (c_i64, []),
     "b200q_log2_round_threshold_bits": (C.c_uint32, [C.c_int]),
     "b200q_log2_floor_threshold_bits": (C.c_uint32, [C.c_int]),
+    "b200q_log2_round_threshold_bits_dt": (C.c_uint32, [C.c_int, C.c_int]),
+    "b200q_log2_floor_threshold_bits_dt": (C.c_uint32, [C.c_int, C.c_int]),
     "b200q_col_absmax": (C.c_int, [c_vp, c_i64, c_i64, c_i64, C.c_int, c_fp, C.c_int, c_vp]),
     "b200q_gptq_parity_quant": (C.c_int, [c_vp, c_vp, c_vp, c_fp, c_fp, c_i64, c_i64, c_i64,
                                           C.c_int, C.c_int, c_vp]),

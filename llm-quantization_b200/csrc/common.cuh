@@ -258,7 +258,7 @@ int launch_awq_delta(const void* W, void* D, const uint8_t* salient, int64_t N, 
                      cudaStream_t st);
 
 // host tables of torch-CPU log2 semantics (log2_tables.cpp)
-const uint32_t* log2_round_thresholds();  // index e+127, e in [-127,127]
-const uint32_t* log2_floor_thresholds();  // index e+149, e in [-149,127]
+const uint32_t* log2_round_thresholds(int dtype);  // index e+127, e in [-127,127]
+const uint32_t* log2_floor_thresholds(int dtype);  // index e+149, e in [-149,127]
 
 }  // namespace b200q

@@ -80,30 +80,87 @@ static uint32_t first_bits_where(Pred pred) {
   return lo;
 }
 
-static uint32_t g_round_thr[255];
-static uint32_t g_floor_thr[277];
+// For fp16 / bf16 tensors torch evaluates log2 in fp32 and rounds the result to the tensor's type
+// before round()/floor() see it, and the argument itself is a 16-bit value: the steps sit
+// elsewhere.  Their tables are built by walking every positive finite value of the type.
+static float round_to_bf16(float f) {
+  uint32_t b;
+  std::memcpy(&b, &f, 4);
+  if ((b & 0x7f800000u) == 0x7f800000u) return f;            // inf / nan
+  b += 0x7fffu + ((b >> 16) & 1u);                             // round to nearest even
+  b &= 0xffff0000u;
+  std::memcpy(&f, &b, 4);
+  return f;
+}
+static float f16_bits_to_f32(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  const uint32_t exp = (h >> 10) & 0x1f, man = h & 0x3ffu;
+  float v;
+  if (exp == 0) v = std::ldexp((float)man, -24);
+  else if (exp == 31) v = man ? NAN : INFINITY;
+  else v = std::ldexp((float)(man | 0x400u), (int)exp - 25);
+  uint32_t b;
+  std::memcpy(&b, &v, 4);
+  b |= sign;
+  std::memcpy(&v, &b, 4);
+  return v;
+}
+static float round_to_f16(float f) {
+  if (!(std::fabs(f) <= 3.4e38f) || f == 0.f) return f;       // nan / inf / zero
+  const float a = std::fabs(f);
+  if (a >= 65520.f) return std::copysign(INFINITY, f);         // rounds past the largest half
+  int e;
+  std::frexp(a, &e);                                           // a = m * 2^e, m in [0.5, 1)
+  const int ulp_exp = std::max(e - 11, -24);                   // 11 significant bits, subnormal floor
+  const float q = std::nearbyint(std::ldexp(a, -ulp_exp));     // ties to even (default mode)
+  return std::copysign(std::ldexp(q, ulp_exp), f);
+}
+
+static uint32_t g_round_thr[3][255];
+static uint32_t g_floor_thr[3][277];
 static std::once_flag g_tables_once;
 
 static void build_tables() {
   for (int e = -127; e <= 127; ++e) {
     const float target = static_cast<float>(e + 1);
-    g_round_thr[e + 127] =
+    g_round_thr[0][e + 127] =
         first_bits_where([&](uint32_t b) { return std::nearbyintf(log2f_model(b)) >= target; });
   }
   for (int e = -149; e <= 127; ++e) {
     const float target = static_cast<float>(e);
-    g_floor_thr[e + 149] =
+    g_floor_thr[0][e + 149] =
         first_bits_where([&](uint32_t b) { return std::floor(log2f_model(b)) >= target; });
+  }
+  // 16-bit types: one pass over all positive finite values in increasing order
+  for (int dt = 1; dt <= 2; ++dt) {
+    for (int i = 0; i < 255; ++i) g_round_thr[dt][i] = 0x7f800000u;
+    for (int i = 0; i < 277; ++i) g_floor_thr[dt][i] = 0x7f800000u;
+    const uint32_t last = dt == 1 ? 0x7bffu : 0x7f7fu;
+    for (uint32_t v = 1; v <= last; ++v) {
+      const float r = dt == 1 ? f16_bits_to_f32((uint16_t)v) : [&]() {
+        uint32_t b = v << 16; float f; std::memcpy(&f, &b, 4); return f; }();
+      uint32_t rbits;
+      std::memcpy(&rbits, &r, 4);
+      float y = log2f_model(rbits);
+      y = dt == 1 ? round_to_f16(y) : round_to_bf16(y);
+      const int ri = (int)std::nearbyintf(y), fi = (int)std::floor(y);
+      // first value whose rounded log2 reaches e+1 / whose floored log2 reaches e, for every e
+      // not yet claimed (values come in increasing order, the results are monotone)
+      for (int e = ri - 1; e >= -127 && e <= 127 && g_round_thr[dt][e + 127] == 0x7f800000u; --e)
+        g_round_thr[dt][e + 127] = rbits;
+      for (int e = fi; e >= -149 && e <= 127 && g_floor_thr[dt][e + 149] == 0x7f800000u; --e)
+        g_floor_thr[dt][e + 149] = rbits;
+    }
   }
 }
 
-const uint32_t* log2_round_thresholds() {
+const uint32_t* log2_round_thresholds(int dtype) {
   std::call_once(g_tables_once, build_tables);
-  return g_round_thr;
+  return g_round_thr[dtype];
 }
-const uint32_t* log2_floor_thresholds() {
+const uint32_t* log2_floor_thresholds(int dtype) {
   std::call_once(g_tables_once, build_tables);
-  return g_floor_thr;
+  return g_floor_thr[dtype];
 }
 
 }  // namespace b200q
@@ -146,13 +203,15 @@ int b200q_profile_query(const char* name, double* total_ms, int64_t* launches, d
   return B200Q_OK;
 }
 
-uint32_t b200q_log2_round_threshold_bits(int e) {
-  if (e < -127 || e > 127) return 0;
-  return b200q::log2_round_thresholds()[e + 127];
+uint32_t b200q_log2_round_threshold_bits(int e) { return b200q_log2_round_threshold_bits_dt(e, 0); }
+uint32_t b200q_log2_floor_threshold_bits(int e) { return b200q_log2_floor_threshold_bits_dt(e, 0); }
+uint32_t b200q_log2_round_threshold_bits_dt(int e, int dtype) {
+  if (e < -127 || e > 127 || dtype < 0 || dtype > 2) return 0;
+  return b200q::log2_round_thresholds(dtype)[e + 127];
 }
-uint32_t b200q_log2_floor_threshold_bits(int e) {
-  if (e < -149 || e > 127) return 0;
-  return b200q::log2_floor_thresholds()[e + 149];
+uint32_t b200q_log2_floor_threshold_bits_dt(int e, int dtype) {
+  if (e < -149 || e > 127 || dtype < 0 || dtype > 2) return 0;
+  return b200q::log2_floor_thresholds(dtype)[e + 149];
 }
 
 }  // extern "C"

@@ -310,6 +310,28 @@ def golden_pot(store: dict) -> None:
         store[f"pot/{name}/scale"] = orc["scale"].numpy()
         store[f"pot/{name}/best_idx"] = orc["best_idx"].numpy()
         store[f"pot/{name}/meta"] = np.array([b, G])
+    # fp16 / bf16 weights: torch evaluates every op in the tensor dtype (config.json:61 is float16)
+    for i, (name, dt, shape, b, G, mul) in enumerate([
+        ("f16_b4_g128", "f16", (8, 256), 4, 128, 1.0),
+        ("bf16_b4_g128", "bf16", (8, 256), 4, 128, 1.0),
+        ("f16_b3_g64", "f16", (8, 128), 3, 64, 20.0),
+        ("bf16_b4_row96", "bf16", (6, 96), 4, -1, 1.0),
+        ("f16_b4_g128_small", "f16", (4, 128), 4, 128, 1e-3),   # ratios underflow in fp16
+        ("f16_b4_g20", "f16", (4, 40), 4, 20, 1.0),             # one ATen vector + scalar tail
+    ]):
+        w = (gen(550 + i, *shape) * mul).to(DT[dt])
+        if name == "f16_b4_g128":
+            w[0, :128] = 0.0
+            w[1, 3] = 0.0
+        ref = ref_pot.pot_quantize_tensor(w.clone(), n_bit=b, q_group_size=G)
+        orc = O.pot_quant(w.clone(), b, G)
+        must_equal(orc["out"], ref, f"pot/{name}")
+        store[f"pot/{name}/w"] = npy(w)
+        store[f"pot/{name}/out"] = npy(ref)
+        store[f"pot/{name}/exps"] = orc["exps"].numpy().astype(np.uint8)
+        store[f"pot/{name}/scale"] = orc["scale"].numpy()
+        store[f"pot/{name}/best_idx"] = orc["best_idx"].numpy()
+        store[f"pot/{name}/meta"] = np.array([b, G])
     store["pot/grid"] = O.pot_grid().numpy()
 
 
@@ -327,6 +349,25 @@ def golden_apot(store: dict) -> None:
         if name == "f32_b4k2_g128":
             w[0, :128] = 0.0
             w[1, 7] = 0.0
+        ref = ref_pot.apot_quantize_tensor(w.clone(), n_bit=b, q_group_size=G, k=k)
+        orc = O.apot_quant(w.clone(), b, G, k)
+        must_equal(orc["out"], ref, f"apot/{name}")
+        store[f"apot/{name}/w"] = npy(w)
+        store[f"apot/{name}/out"] = npy(ref)
+        store[f"apot/{name}/level_idx"] = orc["level_idx"].numpy().astype(np.uint8)
+        store[f"apot/{name}/scale"] = orc["scale"].numpy()
+        store[f"apot/{name}/best_idx"] = orc["best_idx"].numpy()
+        store[f"apot/{name}/levels"] = orc["levels"].numpy()
+        store[f"apot/{name}/meta"] = np.array([b, G, k])
+    for i, (name, dt, shape, b, G, k, mul) in enumerate([
+        ("f16_b4k2_g128", "f16", (8, 256), 4, 128, 2, 1.0),
+        ("bf16_b4k2_g128", "bf16", (8, 256), 4, 128, 2, 1.0),
+        ("f16_b8k2_g64", "f16", (8, 128), 8, 64, 2, 30.0),
+        ("bf16_b4k2_row96", "bf16", (6, 96), 4, -1, 2, 1.0),
+    ]):
+        w = (gen(660 + i, *shape) * mul).to(DT[dt])
+        if name == "f16_b4k2_g128":
+            w[0, :128] = 0.0
         ref = ref_pot.apot_quantize_tensor(w.clone(), n_bit=b, q_group_size=G, k=k)
         orc = O.apot_quant(w.clone(), b, G, k)
         must_equal(orc["out"], ref, f"apot/{name}")

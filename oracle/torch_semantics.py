@@ -78,6 +78,62 @@ def rowsum_model(x: np.ndarray, V: int = 8) -> np.ndarray:
     return total
 
 
+def rowsum_model16(x: np.ndarray) -> np.ndarray:
+    """fp32 row sums (before the final rounding to the tensor dtype) of x [rows, G] holding fp16 /
+    bf16 VALUES, in the order ATen uses for 16-bit input: a load brings 16 elements and returns the
+    8-lane fp32 vector low8 + high8; those vectors then go through the same 4-accumulator cascade
+    as fp32 input; rows shorter than 16 use 4 interleaved scalar accumulators."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    rows, G = x.shape
+    if G < 16:
+        return rowsum_model(x, V=1 << 30)          # forces the scalar_inner_sum branch
+    nv = G // 16
+    vecs = np.concatenate([(x[:, j * 16:j * 16 + 8] + x[:, j * 16 + 8:j * 16 + 16]).astype(np.float32)
+                           for j in range(nv)], axis=1)
+    head = rowsum_model_parts(vecs)                 # [rows, 8] lane totals, not yet added up
+    total = np.zeros(rows, np.float32)
+    for t in range(nv * 16, G):
+        total += x[:, t]
+    for lane in range(8):
+        total += head[:, lane]
+    return total
+
+
+def rowsum_model_parts(x: np.ndarray, V: int = 8) -> np.ndarray:
+    """The 8 lane totals ATen holds before its final horizontal add (x is [rows, n*V])."""
+    rows, G = x.shape
+    vec_size = G // V
+    ilp, num_levels = 4, 4
+    size_ilp = vec_size // ilp
+    level_power = max(4, _ceil_log2(size_ilp) // num_levels)
+    level_step = 1 << level_power
+    level_mask = level_step - 1
+    acc = np.zeros((num_levels, ilp, rows, V), np.float32)
+    i = 0
+    while i + level_step <= size_ilp:
+        for _ in range(level_step):
+            for k in range(ilp):
+                acc[0, k] += x[:, (i * ilp + k) * V:(i * ilp + k + 1) * V]
+            i += 1
+        for j in range(1, num_levels):
+            acc[j] += acc[j - 1]
+            acc[j - 1] = 0
+            if (i & (level_mask << (j * level_power))) != 0:
+                break
+    while i < size_ilp:
+        for k in range(ilp):
+            acc[0, k] += x[:, (i * ilp + k) * V:(i * ilp + k + 1) * V]
+        i += 1
+    for j in range(1, num_levels):
+        acc[0] += acc[j]
+    part = acc[0]
+    for vi in range(size_ilp * ilp, vec_size):
+        part[0] += x[:, vi * V:(vi + 1) * V]
+    for k in range(1, ilp):
+        part[0] += part[k]
+    return part[0]
+
+
 def _log2f_model(bits: np.ndarray) -> np.ndarray:
     r = bits.astype(np.uint32).view(np.float32)
     with np.errstate(divide="ignore"):

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import case_dtype
 from oracle import quant_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -28,8 +29,8 @@ def test_pot_golden(golden):
     assert np.array_equal(grid.numpy(), g.arr("pot/grid"))
     for case in g.cases("pot"):
         b, G = (int(v) for v in g.arr(f"pot/{case}/meta"))
-        w = g.tensor(f"pot/{case}/w")
-        want = g.tensor(f"pot/{case}/out")
+        w = g.tensor(f"pot/{case}/w", case_dtype(case))
+        want = g.tensor(f"pot/{case}/out", case_dtype(case))
         same(pot_quantize_tensor(w.cuda(), n_bit=b, q_group_size=G), want, case)
         same(pot_quantize_tensor(w, n_bit=b, q_group_size=G), want, case + " (host tensor in)")
         groups = w.cuda().reshape(-1, G) if G > 0 else w.cuda()
@@ -87,8 +88,8 @@ def test_apot_golden(golden):
         if case == "big":
             continue
         b, G, k = (int(v) for v in g.arr(f"apot/{case}/meta"))
-        w = g.tensor(f"apot/{case}/w")
-        want = g.tensor(f"apot/{case}/out")
+        w = g.tensor(f"apot/{case}/w", case_dtype(case))
+        want = g.tensor(f"apot/{case}/out", case_dtype(case))
         assert torch.equal(_apot_signed_levels(b, k), g.tensor(f"apot/{case}/levels"))
         same(apot_quantize_tensor(w.cuda(), n_bit=b, q_group_size=G, k=k), want, case)
         groups = w.cuda().reshape(-1, G) if G > 0 else w.cuda()
@@ -166,3 +167,39 @@ def test_pot_apot_model_walkers():
         same(net[0].weight.data, orc(w0[0]))
         same(net[2].weight.data, orc(w0[1]))
         assert net[0].weight.data.is_cuda
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape,b,G,mul", [((128, 1024), 4, 128, 1.0), ((32, 256), 3, 128, 40.0),
+                                           ((16, 768), 4, -1, 1.0), ((12, 200), 4, 40, 1.0),
+                                           ((9, 60), 4, 12, 1.0), ((16, 256), 4, 128, 2e-3)])
+def test_pot_16bit_vs_oracle(dtype, shape, b, G, mul):
+    from b200q import ops
+    g = torch.Generator().manual_seed(abs(hash((shape, b, G, str(dtype)))) % 2**31)
+    w = (torch.randn(*shape, generator=g) * 0.02 * mul).to(dtype)
+    w[0, :3] = 0
+    r = O.pot_quant(w, b, G)
+    groups = w.cuda().reshape(-1, G) if G > 0 else w.cuda()
+    out, exps, scale, idx = ops.pot_quant(groups, b, O.pot_grid(), return_codes=True)
+    assert torch.equal(idx.cpu(), r["best_idx"]), "chosen grid point differs"
+    assert torch.equal(exps.cpu().reshape(shape).to(torch.int32), r["exps"])
+    assert torch.equal(scale.cpu(), r["scale"])
+    same(out.reshape(shape), r["out"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape,b,G,k", [((128, 1024), 4, 128, 2), ((32, 256), 8, 128, 2),
+                                         ((16, 768), 4, -1, 2), ((12, 200), 4, 40, 2)])
+def test_apot_16bit_vs_oracle(dtype, shape, b, G, k):
+    from pot_apot_quantizer import _apot_signed_levels
+    from b200q import ops
+    g = torch.Generator().manual_seed(abs(hash((shape, b, G, k, str(dtype)))) % 2**31)
+    w = (torch.randn(*shape, generator=g) * 0.02).to(dtype)
+    r = O.apot_quant(w, b, G, k)
+    groups = w.cuda().reshape(-1, G) if G > 0 else w.cuda()
+    out, lidx, scale, idx = ops.apot_quant(groups, _apot_signed_levels(b, k), O.apot_grid(w.numel()),
+                                           return_codes=True)
+    assert torch.equal(idx.cpu(), r["best_idx"]), "chosen grid point differs"
+    assert torch.equal(lidx.cpu().reshape(shape).to(torch.int32), r["level_idx"])
+    assert torch.equal(scale.cpu(), r["scale"])
+    same(out.reshape(shape), r["out"])

@@ -96,8 +96,8 @@ def test_pot_matches_reference(golden):
     assert np.array_equal(O.pot_grid().numpy(), g.arr("pot/grid"))
     for case in g.cases("pot"):
         b, G = (int(v) for v in g.arr(f"pot/{case}/meta"))
-        r = O.pot_quant(g.tensor(f"pot/{case}/w"), b, G)
-        _same(r["out"], g.tensor(f"pot/{case}/out"))
+        r = O.pot_quant(g.tensor(f"pot/{case}/w", case_dtype(case)), b, G)
+        _same(r["out"], g.tensor(f"pot/{case}/out", case_dtype(case)))
         assert np.array_equal(r["exps"].numpy().astype(np.uint8), g.arr(f"pot/{case}/exps"))
         assert np.array_equal(r["best_idx"].numpy(), g.arr(f"pot/{case}/best_idx"))
 
@@ -108,8 +108,8 @@ def test_apot_matches_reference(golden):
         if case == "big":
             continue
         b, G, k = (int(v) for v in g.arr(f"apot/{case}/meta"))
-        r = O.apot_quant(g.tensor(f"apot/{case}/w"), b, G, k)
-        _same(r["out"], g.tensor(f"apot/{case}/out"))
+        r = O.apot_quant(g.tensor(f"apot/{case}/w", case_dtype(case)), b, G, k)
+        _same(r["out"], g.tensor(f"apot/{case}/out", case_dtype(case)))
         assert np.array_equal(r["level_idx"].numpy().astype(np.uint8), g.arr(f"apot/{case}/level_idx"))
     for key in [k for k in g.z.files if k.startswith("apot_levels/")]:
         n, k = (int(v[1:]) for v in key.split("/")[1].split("_"))

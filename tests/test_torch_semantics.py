@@ -69,3 +69,38 @@ def test_pot_exponent_rule_matches_torch_on_random_ratios():
         t = np.where(e < emax, thr[np.minimum(e, 126)], 0xFFFFFFFF)
         got = e + (bits >= t)
         assert np.array_equal(want.astype(np.int64), got)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("G", [1, 5, 12, 15, 16, 24, 40, 96, 100, 128, 200, 256, 768, 4096])
+def test_rowsum_order_model_16bit_is_torchs(dtype, G):
+    g = torch.Generator().manual_seed(G + 1)
+    for rows in (1, 6, 500):
+        x = ((torch.randn(rows, G, generator=g) * 0.02) ** 2).to(dtype)
+        want = x.sum(dim=1)
+        got = torch.from_numpy(TS.rowsum_model16(x.float().numpy())).to(dtype)
+        assert torch.equal(want, got), f"{dtype} G={G} rows={rows}"
+
+
+@pytest.mark.parametrize("dtype,code", [(torch.float16, 1), (torch.bfloat16, 2)])
+def test_log2_steps_16bit_match_torch_and_library(dtype, code):
+    """Every positive finite fp16 / bf16 value: rne(log2(r)) and floor(log2(r)) evaluated in that
+    dtype by torch step exactly where the library's per-dtype tables say."""
+    lib = _lib.load()
+    if dtype == torch.float16:
+        vals = torch.arange(1, 0x7C00, dtype=torch.int32).to(torch.int16).view(torch.float16)
+    else:
+        vals = torch.arange(1, 0x7F80, dtype=torch.int32).to(torch.int16).view(torch.bfloat16)
+    lg = torch.log2(vals)
+    R = torch.round(lg).float().numpy()
+    F = torch.floor(lg).float().numpy()
+    bits = vals.float().numpy().view(np.int32).astype(np.int64)
+    assert (np.diff(R) >= 0).all() and (np.diff(F) >= 0).all()
+    for e in range(-127, 128):
+        hit = np.nonzero(R >= e + 1)[0]
+        want = int(bits[hit[0]]) if len(hit) else 0x7F800000
+        assert lib.b200q_log2_round_threshold_bits_dt(e, code) == want, f"round e={e}"
+    for e in range(-149, 128):
+        hit = np.nonzero(F >= e)[0]
+        want = int(bits[hit[0]]) if len(hit) else 0x7F800000
+        assert lib.b200q_log2_floor_threshold_bits_dt(e, code) == want, f"floor e={e}"
