@@ -480,10 +480,20 @@ def main():
                 return sum(1 for m in range(tm) for n in range(tn) if (n + 1) * 256 > m * 128) / (tm * tn)
             wsum = sum(K * K for _, _, K in layers)
             exe = sum(K * K * executed_fraction(K) for _, _, K in layers) / wsum
+            # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel at
+            # the same token count (profiles/traffic_r1.json), averaged over this model's layers
+            traffic = None
+            tj = REPO / "profiles" / "traffic_r1.json"
+            if tj.exists() and world == 1:
+                tr = json.loads(tj.read_text())
+                byK = tr.get("dram_bytes_per_launch_by_K", {})
+                if tr.get("tokens") == tokens_total and all(str(K) in byK for _, _, K in layers):
+                    traffic = sum(byK[str(K)] for _, _, K in layers) / len(layers)
             roofline = {"bound": "tensor", "kernel": dom_name, "achieved": ach, "peak": peak,
                         "unit": "TFLOP/s", "frac": ach / peak,
                         "peak_source": src + ", sustained bf16 (kernel timed inside a long step)",
-                        "traffic": None, "launches_timed": q["launches"], "avg_launch_ms": avg_ms,
+                        "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write)",
+                        "launches_timed": q["launches"], "avg_launch_ms": avg_ms,
                         "algorithmic_flops_per_launch": q["flops"] / q["launches"],
                         "executed_mma_fraction": exe, "executed_tflops": ach * exe,
                         "executed_frac_of_peak": ach * exe / peak,
