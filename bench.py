@@ -160,7 +160,8 @@ def make_step(method: str, acts_by_K, stats_by_K, act_scale_by_K):
     if method == "awq":
         def step(model):
             # (a10) per-batch mean|x| statistics, as the calibration hooks would collect them
-            stats = {K: ops.act_meanabs_batched(x).to(x.dtype) for K, x in acts_by_K.items()}
+            # (a data-parallel calibration run produces them per rank: batches dealt, rows gathered)
+            stats = {K: awq_quantizer._stat_rows(x, x.device) for K, x in acts_by_K.items()}
             # (a9) 20-point grid search on the raw activations, (a8) quantize with the winner
             best = awq_quantizer.awq_search_scale_factor(model, W_BIT, GROUP, by_layer(model, acts_by_K),
                                                          protect_ratio=0.01, n_grid=N_GRID)

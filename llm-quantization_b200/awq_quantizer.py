@@ -46,8 +46,12 @@ def _stat_rows(feats: List[torch.Tensor], device) -> torch.Tensor:
     """[n, K] matrix of per-batch mean|x| rows from a feature list whose entries are either such
     vectors already (1-D) or raw [tokens, K] activations (reduced by the act_meanabs kernel)."""
     if isinstance(feats, torch.Tensor) and feats.dim() == 3:
-        # [n, tokens, K] batch of raw activations: one batched reduction
-        return _ops.act_meanabs_batched(_ops.to_device(feats)).to(feats.dtype)
+        # [n, tokens, K] batch of raw activations: one batched reduction (under row sharding the
+        # batches are dealt to the ranks and the [n, K] rows all-gathered)
+        from b200q import dist as _dist
+        x = _ops.to_device(feats)
+        return _dist.gather_rows(lambda lo, hi: _ops.act_meanabs_batched(x[lo:hi]), x.shape[0],
+                                 (x.shape[2],), torch.float32, x.device).to(feats.dtype)
     rows = []
     for f in feats:
         if f.dim() == 1:

@@ -71,6 +71,20 @@ def broadcast(t: torch.Tensor, src: int = 0) -> torch.Tensor:
     return t
 
 
+def gather_rows(compute, n_rows: int, row_shape, dtype, device) -> torch.Tensor:
+    """[n_rows, *row_shape] tensor whose rows are produced by `compute(lo, hi)` (-> rows lo..hi-1):
+    under sharding each rank computes an equal share and the shares are all-gathered; otherwise (or
+    when n_rows does not divide evenly) the caller's rank computes everything."""
+    if not is_sharded() or n_rows % world_size() != 0:
+        return compute(0, n_rows)
+    w, r = world_size(), rank()
+    per = n_rows // w
+    local = compute(r * per, (r + 1) * per).contiguous()
+    out = torch.empty((n_rows, *row_shape), dtype=dtype, device=device)
+    td.all_gather_into_tensor(out, local, group=_active_group)
+    return out
+
+
 def global_numel(local_numel: int, device) -> int:
     """Element count of the whole (unsharded) tensor."""
     if not is_sharded():
