@@ -513,6 +513,16 @@ def main():
                   **({"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12} if v["flops"] > 0 and v["ms"] > 0 else {}),
                   **({"gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9} if v["bytes"] > 0 and v["ms"] > 0 else {})}
               for n, v in kq.items() if v["launches"] > 0}
+    if "awq_search_gemm" in stages and "tflops" in stages["awq_search_gemm"]:
+        # the search GEMM multiplies by H folded onto its lower triangle and stops each output
+        # tile's k-loop at the tile's right edge: it executes about half of the algorithmic flops
+        def tri_fraction(K):
+            tn = -(-K // 256)
+            return sum(min(K, (j + 1) * 256) for j in range(tn)) / (tn * K)
+        wsum = sum(N * K * K for _, N, K in layers)
+        fr = sum(N * K * K * tri_fraction(K) for _, N, K in layers) / wsum
+        stages["awq_search_gemm"]["executed_mma_fraction"] = fr
+        stages["awq_search_gemm"]["executed_tflops"] = stages["awq_search_gemm"]["tflops"] * fr
     cpu = None if args.no_cpu_baseline else cpu_baseline(args.method, args.model, dtype, tokens_total)
     line = {
         "metric": metric, "value": total_rows / (ms_step * 1e-3), "unit": "rows/s",

@@ -270,14 +270,6 @@ __global__ void reverse_both_kernel(const float* __restrict__ src, float* __rest
   }
 }
 
-__global__ void copy_block_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst,
-                                  int64_t ldd, int rows, int cols) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * cols; i += gridDim.x * blockDim.x) {
-    const int r = i / cols, c = i % cols;
-    dst[(int64_t)r * ldd + c] = src[(int64_t)r * lds + c];
-  }
-}
-
 struct LinalgWork {
   float* A;      // [K,K] working copy -> L (lower)
   float* Linv;   // [K,K] -> L^-1 (lower)

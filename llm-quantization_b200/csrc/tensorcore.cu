@@ -161,6 +161,7 @@ constexpr uint32_t TMEM_COLS = 256;
 constexpr int RASTER_M = 16;     // tile rows per rasterisation band
 }  // namespace hg
 
+template <bool BF16>
 __global__ void __launch_bounds__(hg::THREADS, 1)
 hessian_gemm_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ partial,
                     int64_t K, int64_t T, int64_t tokens_per_split, int tiles_n) {
@@ -236,7 +237,7 @@ hessian_gemm_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN, /*bf16=*/false, /*a_mn=*/true, /*b_mn=*/true);
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN, BF16, /*a_mn=*/true, /*b_mn=*/true);
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -309,9 +310,9 @@ hessian_gemm_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
 // 4. split reduction and finalisation
 // =================================================================================================
 __global__ void hessian_reduce_kernel(const float* __restrict__ partial, int splits, int64_t KK,
-                                      const float* __restrict__ stats, int n_samples,
+                                      const float* __restrict__ unscale_ptr,
                                       float* __restrict__ H, int accumulate) {
-  const float unscale = stats[2 * n_samples];
+  const float unscale = unscale_ptr ? *unscale_ptr : 1.f;
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < KK;
        i += (int64_t)gridDim.x * blockDim.x * 4) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -358,14 +359,15 @@ static EncodeTiledFn get_encode_fn() {
 
 // tensor map over a row-major [rows, cols] 16-bit matrix, box = box_rows x 64 columns, 128B swizzle
 static int make_tmap_2d_16bit(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
-                              int box_rows, int box_cols) {
+                              int box_rows, int box_cols, bool bf16 = false) {
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) return fail(B200Q_ECUDA, "cuTensorMapEncodeTiled unavailable");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+  CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                   const_cast<void*>(base), gdim, gstride,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B200Q_ECUDA, "cuTensorMapEncodeTiled failed");
@@ -423,8 +425,9 @@ static HessianWork hessian_layout(void* work, int64_t T, int64_t K, int n_sample
 
 // =================================================================================================
 // AWQ scale search, stage 2: loss_c = sum_rows dW_c H dW_c^T = <dW_c H, dW_c>
-// One tcgen05 GEMM over all candidates stacked along M:  P = D * Hb  (D [n_cand * rows_pad, K]
-// bf16, Hb = bf16(H) [K, K], symmetric so Hb[n, k] serves as the K-major B operand), with the
+// One tcgen05 GEMM over all candidates stacked along M:  P = D * Hb^T  (D [n_cand * rows_pad, K]
+// bf16; Hb [K, K] bf16 is H folded onto its lower triangle, Hb[n, k] being the K-major B operand
+// -- the quadratic form is unchanged and half of the k-blocks drop out), with the
 // dot product <P, D> fused into the epilogue: the 128x256 fp32 tile leaves TMEM, is multiplied
 // with the matching bf16 tile of D and reduced to ONE float per CTA.  Per-candidate sums are
 // formed afterwards in a fixed order (deterministic).
@@ -461,9 +464,13 @@ awq_loss_gemm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_co
   const int band = blockIdx.x / (RASTER_M * tiles_n);
   const int within = blockIdx.x % (RASTER_M * tiles_n);
   const int band_rows = min(RASTER_M, tiles_m - band * RASTER_M);
-  const int n_blk = within / band_rows;
+  // Hb is LOWER triangular (see h_to_lower_bf16_kernel): output columns [n0, n0 + BN) only receive
+  // contributions from k < n0 + BN, so the k-loop of a tile stops there -- half the MMAs of the
+  // dense product overall.  Tiles are issued heaviest (rightmost) first inside every band so the
+  // short ones fill the tail of the wave.
+  const int n_blk = tiles_n - 1 - within / band_rows;
   const int m_blk = band * RASTER_M + within % band_rows;
-  const int num_kb = (int)((K + BK - 1) / BK);
+  const int num_kb = (int)((min(K, (int64_t)(n_blk + 1) * BN) + BK - 1) / BK);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_d);
@@ -550,15 +557,30 @@ awq_loss_gemm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_co
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                   int64_t n) {
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n;
-       i += (int64_t)gridDim.x * blockDim.x * 2) {
-    if (i + 1 < n) {
-      *reinterpret_cast<__nv_bfloat162*>(dst + i) = __floats2bfloat162_rn(src[i], src[i + 1]);
-    } else {
-      dst[i] = __float2bfloat16_rn(src[i]);
-    }
+// Hb[n][k] = bf16(H[n][k] + H[k][n]) for k < n, bf16(H[n][n]) on the diagonal, 0 above it.
+// x H x^T = sum_n x_n (H_nn x_n + sum_{k<n} (H_nk + H_kn) x_k) for ANY square H, so the search GEMM
+// can use this triangular operand and skip the k-blocks right of each output tile.
+__global__ void __launch_bounds__(256)
+h_to_lower_bf16_kernel(const float* __restrict__ H, __nv_bfloat16* __restrict__ Hb, int64_t K) {
+  __shared__ float tile[32][33];
+  const int64_t n0 = (int64_t)blockIdx.y * 32, k0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  if (k0 > n0 + 31) {                                            // entirely above the diagonal
+    for (int r = ty; r < 32; r += 8)
+      if (n0 + r < K && k0 + tx < K) Hb[(n0 + r) * K + k0 + tx] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  // transposed block H[k0.., n0..] through shared memory (coalesced both ways)
+  for (int r = ty; r < 32; r += 8)
+    tile[r][tx] = (k0 + r < K && n0 + tx < K) ? H[(k0 + r) * K + n0 + tx] : 0.f;
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t n = n0 + r, k = k0 + tx;
+    if (n >= K || k >= K) continue;
+    float v = 0.f;
+    if (k < n) v = H[n * K + k] + tile[tx][r];
+    else if (k == n) v = H[n * K + k];
+    Hb[n * K + k] = __float2bfloat16_rn(v);
   }
 }
 
@@ -642,7 +664,12 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
   HessianWork w = hessian_layout(work, T, K, n_samples);
   const double flops = 2.0 * (double)T * (double)K * (double)K;
 
-  {
+  // A plain Gram matrix (no per-sample normalisation, no norms wanted) of 16-bit activations needs
+  // no staging pass at all: fp16 / bf16 products are exact in the fp32 accumulator, so TMA reads the
+  // caller's tensor directly.  Everything else goes through stats + prescale into fp16.
+  const bool direct = !normalize && norms_out == nullptr && (dtype == B200Q_F16 || dtype == B200Q_BF16);
+  const bool bf16_ops = direct && dtype == B200Q_BF16;
+  if (!direct) {
     KernelScope scope("hessian_prescale", 3.0 * T * K * elem_size(dtype), 0, st);
     B200Q_DISPATCH_DTYPE(dtype, Tt, {
       constexpr int VEC = ST<Tt>::VEC;
@@ -666,18 +693,15 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
                     cudaMemcpyDeviceToDevice, st);
 
   CUtensorMap tmap;
-  int rc = make_tmap_2d_16bit(&tmap, w.Xs, T, K, hg::BKT, hg::BOX_CH);
+  int rc = make_tmap_2d_16bit(&tmap, direct ? X : static_cast<const void*>(w.Xs), T, K, hg::BKT,
+                              hg::BOX_CH, bf16_ops);
   if (rc != B200Q_OK) return rc;
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, []() {
-    attr_err = cudaFuncSetAttribute(hessian_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    hg::SMEM_BYTES);
-  });
-  // (per-device attribute: re-apply cheaply every call; the call is idempotent)
-  cudaFuncSetAttribute(hessian_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       hg::SMEM_BYTES);
-  if (attr_err != cudaSuccess) return fail(B200Q_ECUDA, "hessian_gemm: cannot raise shared memory");
+  // (per-device attribute: the call is cheap and idempotent)
+  if (cudaFuncSetAttribute(hessian_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           hg::SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(hessian_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           hg::SMEM_BYTES) != cudaSuccess)
+    return fail(B200Q_ECUDA, "hessian_gemm: cannot raise shared memory");
   const int64_t kblocks = (T + hg::BKT - 1) / hg::BKT;
   const int64_t kb_per_split = (kblocks + w.splits - 1) / w.splits;
   const int64_t tokens_per_split = kb_per_split * hg::BKT;
@@ -686,8 +710,12 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
     const int tiles_n = (int)((K + hg::BN - 1) / hg::BN);
     const int tiles_m = (int)((K + hg::BM - 1) / hg::BM);
     dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)w.splits);
-    hessian_gemm_kernel<<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(tmap, w.partial, K, T,
-                                                                   tokens_per_split, tiles_n);
+    if (bf16_ops)
+      hessian_gemm_kernel<true><<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(tmap, w.partial, K, T,
+                                                                           tokens_per_split, tiles_n);
+    else
+      hessian_gemm_kernel<false><<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(tmap, w.partial, K, T,
+                                                                            tokens_per_split, tiles_n);
     count_launch();
     rc = check_launch("hessian_gemm");
     if (rc != B200Q_OK) return rc;
@@ -696,7 +724,8 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
     KernelScope scope("hessian_reduce", sizeof(float) * (double)(w.splits + 1) * K * K, 0, st);
     const int64_t KK = K * K;
     const int blocks = (int)std::min<int64_t>((KK / 4 + 255) / 256, (int64_t)kNumSMs * 16);
-    hessian_reduce_kernel<<<blocks, 256, 0, st>>>(w.partial, w.splits, KK, w.stats, n_samples, H,
+    hessian_reduce_kernel<<<blocks, 256, 0, st>>>(w.partial, w.splits, KK,
+                                                  direct ? nullptr : w.stats + 2 * n_samples, H,
                                                   accumulate);
     count_launch();
     rc = check_launch("hessian_reduce");
@@ -739,8 +768,8 @@ int b200q_awq_search_loss(const void* W, int64_t N, int64_t K, int64_t group, in
       cudaMemsetAsync(w.D, 0, 2 * Mtot * K, st);
     rc = launch_awq_delta(W, w.D, salient, N, K, w.rows_pad * K, n_bit, sf_host, n_cand, dtype, st);
     if (rc != B200Q_OK) return rc;
-    const int blocks = (int)std::min<int64_t>((K * K / 2 + 255) / 256, (int64_t)kNumSMs * 16);
-    f32_to_bf16_kernel<<<blocks, 256, 0, st>>>(H, w.Hb, K * K);
+    const unsigned tb = (unsigned)((K + 31) / 32);
+    h_to_lower_bf16_kernel<<<dim3(tb, tb), 256, 0, st>>>(H, w.Hb, K);
     count_launch();
   }
   CUtensorMap tmap_d, tmap_h;

@@ -63,3 +63,21 @@ def test_search_entry_point_returns_grid_argmin(capsys):
         assert aq.awq_search_scale_factor(net, 4, 128, {"0": feats}) == 1.5
     finally:
         aq.SEARCH_STUB = False
+
+
+def test_quadratic_form_is_folded_onto_the_lower_triangle():
+    """The search GEMM uses Hb = tril(H + H^T) - diag(H) and skips the k-blocks right of every
+    output tile; x H x^T is unchanged for ANY square H, symmetric or not."""
+    from b200q import tensor_ops as T
+    N, K = 384, 768
+    W, feats, hot = setup(N, K, 99)
+    g = torch.Generator().manual_seed(3)
+    A = torch.randn(K, K, generator=g)
+    H = (A @ A.T / K + 0.3 * torch.randn(K, K, generator=g)).float()     # not symmetric
+    mask = torch.zeros(K, dtype=torch.uint8)
+    mask[hot] = 1
+    cands = torch.linspace(1.0, 2.0, 5, dtype=torch.float64).tolist()
+    got = T.awq_search_losses(W.cuda(), H.cuda(), mask.cuda(), 4, 128, cands).cpu().double()
+    sym = ((H.double() + H.double().T) / 2).float()
+    want = O.awq_search_losses(W, sym, hot, 4, 128, cands)
+    assert ((got - want).abs() / want.abs()).max().item() < 1e-2

@@ -84,3 +84,25 @@ def test_gptq_hessian_ragged_and_identity():
     assert rel_err(H.cpu(), want) < 1e-3
     H = gq.gptq_hessian(["not a tensor"] * 4, K, "cuda", 0.01, 128)
     assert torch.equal(H.cpu(), torch.eye(K) / 4 + 0.01 * torch.eye(K))
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n,rows,K", [(4, 256, 512), (3, 100, 392), (1, 4096, 1024)])
+def test_gram_of_16bit_activations_reads_them_directly(dtype, n, rows, K):
+    """normalize=False on fp16/bf16 input skips the staging pass: products of 16-bit inputs are
+    exact in fp32, so the only error left is the fp32 summation order (1e-5 of the largest entry)."""
+    from b200q import tensor_ops as T
+    from b200q import _lib
+    feats = make_feats(5 + K, n, rows, K, dtype)
+    X = torch.cat(feats).cuda()
+    _lib.profile_enable(True)
+    H = T.hessian_accum(X, rows, normalize=False)
+    torch.cuda.synchronize()
+    ran = {k: _lib.profile_query(k)["launches"] for k in ("hessian_gemm", "hessian_prescale")}
+    _lib.profile_enable(False)
+    assert ran["hessian_gemm"] >= 1 and ran["hessian_prescale"] == 0, ran
+    want = X.cpu().double().T @ X.cpu().double()
+    assert rel_err(H.cpu(), want) < 1e-5
+    assert torch.equal(H, H.T)
+    H2 = T.hessian_accum(X, rows, H.clone(), normalize=False)
+    assert rel_err(H2.cpu(), 2 * want) < 1e-5
