@@ -386,7 +386,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     dom_name, dom_bound = DOMINANT[args.method]
     kq = {n: _lib.profile_query(n) for n in
-          ("hessian_gemm", "hessian_prescale", "hessian_reduce", "awq_search_gemm", "awq_search_delta",
+          ("hessian_gemm", "hessian_prescale", "hessian_reduce", "awq_search_gemm", "awq_search_delta", "awq_search_fold",
            "act_meanabs", "group_fakequant", "gptq_parity_quant", "col_absmax", "spd_inverse",
            "pot_quant", "apot_quant", "seq_sum_rows")}
     kall = _lib.profile_query(None)

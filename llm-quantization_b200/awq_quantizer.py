@@ -119,6 +119,14 @@ def awq_search_scale_factor(
     from b200q import dist as _dist
     candidates = torch.linspace(float(lo), float(hi), int(n_grid), dtype=torch.float64).tolist()
     totals = []
+    items = [(n, m) for n, m in model.named_modules()
+             if isinstance(m, nn.Linear) and n in input_feat]
+    index = {n: i for i, (n, _) in enumerate(items)}
+    grams = {}
+
+    def start_gram(i, device):
+        n, m = items[i]
+        grams[n] = _tops.gram_matrix_begin(input_feat[n], m.weight.shape[1], device)
 
     def compute(name, _module, W):
         K = W.shape[1]
@@ -131,8 +139,19 @@ def awq_search_scale_factor(
             stat_rows = _stat_rows(feats, W.device)
         n_protect = max(1, int(K * protect_ratio))
         mask = _ops.salient_mask(_feat_matrix(stat_rows, W.device), n_protect)
-        H = _tops.gram_matrix(feats, K, W.device)
+        # under row sharding the NEXT layer's partial Gram matrix and its all-reduce are started
+        # before this layer's search runs, so the exchange hides behind the search GEMM
+        i = index[name]
+        if name not in grams:
+            start_gram(i, W.device)
+        if _dist.is_sharded() and i + 1 < len(items):
+            start_gram(i + 1, W.device)
+        # the loss is linear in H: search in the plain sum X^T X and divide the n_grid losses by
+        # the row count instead of rescaling the [K, K] matrix
+        gram = grams.pop(name)
+        H = _tops.gram_matrix_end(gram, normalise=False)
         loss = _tops.awq_search_losses(W, H, mask, w_bit, q_group_size, candidates)
+        loss.mul_(1.0 / gram.rows_total)
         if totals:
             totals[0] += loss
         else:
@@ -140,8 +159,7 @@ def awq_search_scale_factor(
         return None                       # the search leaves the model untouched
 
     # host-resident weights are prefetched one layer ahead; nothing is written back
-    _pipeline.run_layers([(n, m) for n, m in model.named_modules()
-                          if isinstance(m, nn.Linear) and n in input_feat], compute)
+    _pipeline.run_layers(items, compute)
     if not totals:
         best = (lo + hi) / 2.0
     else:

@@ -29,6 +29,7 @@ SOURCES = {
     "levels.cu": ["-fmad=false"],
     "tensorcore.cu": [],
     "linalg.cu": [],
+    "splitgemm.cu": [],
 }
 
 

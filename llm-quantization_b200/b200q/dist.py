@@ -64,6 +64,14 @@ def allreduce_sum(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def allreduce_sum_async(t: torch.Tensor):
+    """Start the sum over ranks of `t` (in place) and return the work handle, or None when not
+    sharded.  handle.wait() orders the caller's current stream after the collective."""
+    if is_sharded():
+        return td.all_reduce(t, op=td.ReduceOp.SUM, group=_active_group, async_op=True)
+    return None
+
+
 def broadcast(t: torch.Tensor, src: int = 0) -> torch.Tensor:
     if is_sharded():
         td.broadcast(t, src=td.get_global_rank(_active_group, src) if _active_group else src,

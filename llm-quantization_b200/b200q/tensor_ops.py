@@ -115,10 +115,18 @@ def gptq_compensated(W: torch.Tensor, H: torch.Tensor, n_bit: int, group: int, b
     return Q.to(W.dtype)
 
 
-def gram_matrix(input_feat: Sequence, in_features: int, device) -> torch.Tensor:
-    """X^T X / (number of rows) over all calibration features of a layer, fp32 [K,K]: the matrix
-    in which the AWQ search measures output reconstruction error.  Feature lists follow the same
-    conventions as gptq_hessian (1-D entries are single rows)."""
+class PendingGram:
+    """A Gram matrix whose cross-rank sum may still be in flight (see gram_matrix_begin)."""
+    __slots__ = ("H", "work", "rows_total")
+
+    def __init__(self, H, work, rows_total):
+        self.H, self.work, self.rows_total = H, work, rows_total
+
+
+def gram_matrix_begin(input_feat: Sequence, in_features: int, device) -> PendingGram:
+    """Launch X^T X over this rank's share of the calibration rows and, under row sharding, START
+    the all-reduce of the partial sums without waiting for it: the caller can queue the next
+    layer's kernels behind this one and pick the result up later with gram_matrix_end."""
     device = torch.device(device)
     K = in_features
     if isinstance(input_feat, torch.Tensor):
@@ -129,21 +137,38 @@ def gram_matrix(input_feat: Sequence, in_features: int, device) -> torch.Tensor:
     if X.dtype not in DTYPE_CODE:
         X = X.float()
     rows_total = X.shape[0]
-    # samples only matter for the fp16 pre-scaling here; use runs of up to 2048 rows
+    # samples only matter for the fp16 pre-scaling of fp32 input here; use runs of up to 2048 rows
     rows = 1
     for cand in (2048, 1024, 512, 256, 128, 64, 32, 16, 8, 4, 2):
         if rows_total % cand == 0:
             rows = cand
             break
+    work = None
     if _dist.is_sharded():
         n = rows_total // rows
         lo, hi = _dist.shard_rows(n, _dist.world_size(), _dist.rank())
         H = hessian_accum(X[lo * rows:hi * rows], rows, normalize=False) if hi > lo else \
             torch.zeros((K, K), dtype=torch.float32, device=device)
-        _dist.allreduce_sum(H)
+        work = _dist.allreduce_sum_async(H)
     else:
         H = hessian_accum(X, rows, normalize=False)
-    return hessian_finalize(H, 1.0 / rows_total, 0.0)
+    return PendingGram(H, work, rows_total)
+
+
+def gram_matrix_end(p: PendingGram, normalise: bool = True) -> torch.Tensor:
+    """The finished matrix: X^T X / rows, or the plain sum X^T X with normalise=False (a caller
+    whose result is linear in H can apply 1 / p.rows_total to its own, much smaller, output)."""
+    if p.work is not None:
+        p.work.wait()                       # orders the current stream after the all-reduce
+        p.work = None
+    return hessian_finalize(p.H, 1.0 / p.rows_total, 0.0) if normalise else p.H
+
+
+def gram_matrix(input_feat: Sequence, in_features: int, device) -> torch.Tensor:
+    """X^T X / (number of rows) over all calibration features of a layer, fp32 [K,K]: the matrix
+    in which the AWQ search measures output reconstruction error.  Feature lists follow the same
+    conventions as gptq_hessian (1-D entries are single rows)."""
+    return gram_matrix_end(gram_matrix_begin(input_feat, in_features, device))
 
 
 def awq_search_losses(W: torch.Tensor, H: torch.Tensor, salient_mask: torch.Tensor, n_bit: int,

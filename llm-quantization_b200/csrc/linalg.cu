@@ -2,22 +2,23 @@
 //
 // H is symmetric positive definite with cond(H) <= (1 + damp)/damp ~ 1e2 by construction (every
 // normalised sample has trace 1), so a Cholesky route is safe and costs K^3
-// flops against LU's 2 K^3:   H = L L^T  ->  L^-1  ->  H^-1 = L^-T L^-1.
-// Blocked right-looking factorisation, NB = 128:
-//   diag  : one CTA factors the 128x128 diagonal block in shared memory and inverts it
-//   panel : L21 = A21 * L11^-T                      (GEMM with the inverted diagonal block)
-//   trail : A22 -= L21 * L21^T  (lower tiles only)   (GEMM, the K^3/3 bulk)
-// The triangular inverse and the final product are row-block sweeps of the same GEMM.
-// All arithmetic is fp32 on the FP32 pipe (8x8 register tiles, 128x128x16 CTA tiles): the
-// factorisation of a matrix that is later used to propagate quantisation errors needs fp32
-// mantissas, and TF32 tensor-core inputs (10 bits) do not provide them.
+// flops against LU's 2 K^3:   H = L L^T  ->  M = L^-1  ->  H^-1 = M^T M.
+// The factorisation is RECURSIVE (factor_inv below): a block is halved, the first half factored
+// and inverted, the panel and the trailing update formed as two large products, the second half
+// factored, and the off-diagonal block of M as two more products.  Those products -- nearly all of
+// the K^3 work -- and the final M^T M run on the tcgen05 tensor cores with fp32 operands split
+// into fp16 planes and round-to-nearest accumulation across k-chunks (splitgemm.cu).  Blocks of
+// <= 512 columns are factored on the FP32 pipe: a one-CTA register-resident kernel per 64 x 64
+// diagonal block, SIMT GEMMs (8x8 register tiles, 128x128x16 CTA tiles) for the rest.
 //
 // For the error-compensated GPTQ loop the quantity needed is U = chol(H^-1, upper).  With J the
 // index reversal, J H J = Lr Lr^T gives H = R R^T with R = J Lr J upper triangular, hence
 // H^-1 = R^-T R^-1 and U = R^-1 = J Lr^-1 J: the same factor-and-invert on the reversed matrix.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
+#include "splitgemm.cuh"
 
 namespace b200q {
 
@@ -147,115 +148,118 @@ static void sgemm(cudaStream_t st, int M, int N, int Kd, float alpha, const floa
   count_launch();
 }
 
-// One CTA of 128 threads: Cholesky of the nb x nb (nb <= 128) diagonal block at A (lower, in place;
-// the strict upper part of the block is zeroed) and its inverse into Linv (dense nb x nb copy,
-// ld = NB) and Linv_big (ld = lda).  info = first non-positive pivot (1-based, offset by j0).
+// One CTA: Cholesky of the nb x nb (nb <= 64) diagonal block at A (lower, in place; the strict
+// upper part of the block is zeroed) and its inverse into Linv (dense copy, ld = NB) and Linv_big
+// (ld = lda).  info = first non-positive pivot (1-based, offset by j0).
 //
-// Left-looking: in step k the threads of row r form A[r][k] - sum_{j<k} L[r][j] L[k][j] from
-// their own row and the pivot row (a broadcast), and accumulate the pivot's own sum in the same
-// loop, so every thread knows sqrt(pivot) without an exchange: two barriers per column and no
-// rank-1 sweeps.  The inverse is a forward substitution per column.  This kernel sits on the
-// critical path K/128 times, so its latency decides the factorisation time for K <= ~8K.
-__global__ void __launch_bounds__(512)
+// This kernel sits on the critical path K/64 times, so its LATENCY decides the factorisation time
+// (ncu on the earlier shared-memory versions: one SM, <20 % issue utilisation, ~1000 cycles per
+// column).  Here the whole block lives in REGISTERS: 256 threads, thread (r, q) holds the 16
+// entries [16q, 16q+16) of row r of A and, later, of L^-1.  Both phases are fully unrolled over the
+// 64 columns so every register index is static:
+//   factor : right-looking.  The owners of column j publish it (rows > j, zeros elsewhere) and the
+//            pivot through shared memory; after ONE barrier every thread applies
+//            a[r][c] -= (a[r][j] / d) * a[c][j] to its 16 columns.  The zeros make the update a
+//            no-op for finished rows and columns, so no predicates are needed.
+//   invert : column sweep.  Row k of L^-1 becomes final at step k (divide by L[k][k]), is
+//            published, and every later row subtracts L[r][k] times it; L[r][k] comes from the
+//            team-mate that owns column k by a shuffle.
+// One barrier per column per phase, buffers double-buffered.  Blocks with nb < 64 are padded with
+// the identity.
+__global__ void __launch_bounds__(256, 1)
 potrf_inv_diag_kernel(float* __restrict__ A, int64_t lda, int nb, float* __restrict__ Linv,
                       float* __restrict__ Linv_big, int* __restrict__ info, int j0) {
-  // FOUR threads per row (512 threads, 16 warps = 4 per scheduler): ncu on the one-thread-per-row
-  // version showed 19 % issue utilisation, every instruction waiting ~5 cycles on the previous one
-  // with a single warp per scheduler.  The 4 lanes of a row take j = q, q+4, ... and combine with
-  // two shuffles.  LD = 132 (= 4 mod 32) makes (row, q) -> bank 4*row + q conflict free.
-  extern __shared__ float sm[];
-  constexpr int LD = la::NB + 4;
-  float* L = sm;                 // [NB][LD]
-  float* X = sm + la::NB * LD;   // [NB][LD]
-  const int tid = threadIdx.x;
-  for (int i = tid; i < la::NB * la::NB; i += blockDim.x) {
-    const int r = i / la::NB, c = i % la::NB;
-    L[r * LD + c] = (r < nb && c <= r) ? A[(int64_t)r * lda + c] : (r == c ? 1.f : 0.f);
-    X[r * LD + c] = 0.f;
+  constexpr int NB = la::NB;
+  static_assert(NB == 64, "register layout assumes 64 x 64 blocks, 16 columns per thread");
+  __shared__ __align__(16) float colbuf[2][NB];
+  __shared__ __align__(16) float rowbuf[2][NB];
+  __shared__ float pivbuf[2];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int r = tid >> 2, q = tid & 3, c0 = q * 16;
+  float a[16], x[16];
+  float my_rinv = 1.f;                                   // 1 / L[r][r]
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = c0 + i;
+    a[i] = (r < nb && c < nb) ? (c <= r ? A[(int64_t)r * lda + c] : 0.f) : (r == c ? 1.f : 0.f);
+    x[i] = (c == r) ? 1.f : 0.f;
   }
-  __syncthreads();
-  const int r = tid >> 2, q = tid & 3;
-  for (int k = 0; k < nb; ++k) {
-    float t = 0.f, d = 0.f;
-    const float* lr = L + r * LD;
-    const float* lk = L + k * LD;
-    // batches of 8 predicated loads first, FMAs after: the trip count is short (<= 32) and a
-    // rolled load->FMA loop would pay the full shared-memory latency on every iteration
-    float t1 = 0.f, d1 = 0.f;
-    for (int base = q; base < k; base += 32) {
-      float a[8], p[8];
+  // (unrolled over the 16 columns of a chunk only: register indices stay static, and the code is a
+  // quarter of the fully unrolled size -- this kernel runs once per launch, so its cost is as much
+  // instruction fetch as arithmetic)
+#pragma unroll 1
+  for (int oq = 0; oq < 4; ++oq)
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int j = base + 4 * u;
-        const bool ok = j < k;
-        a[u] = ok ? lr[j] : 0.f;
-        p[u] = ok ? lk[j] : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; u += 2) {
-        t = fmaf(-a[u], p[u], t);
-        t1 = fmaf(-a[u + 1], p[u + 1], t1);
-        d = fmaf(-p[u], p[u], d);
-        d1 = fmaf(-p[u + 1], p[u + 1], d1);
-      }
-    }
-    t += t1;
-    d += d1;
-    t += __shfl_xor_sync(0xffffffffu, t, 1);
-    d += __shfl_xor_sync(0xffffffffu, d, 1);
-    t += __shfl_xor_sync(0xffffffffu, t, 2);
-    d += __shfl_xor_sync(0xffffffffu, d, 2);
-    t += lr[k];                            // A[r][k] - sum_j L[r][j] L[k][j]
-    d += lk[k];                            // A[k][k] - sum_j L[k][j]^2
-    const float piv = sqrtf(fmaxf(d, 1e-30f));
-    if (tid == 0 && !(d > 0.f) && info != nullptr) atomicCAS(info, 0, j0 + k + 1);
-    __syncthreads();                       // everyone has read column k of A / row k of L
-    if (q == 0) {
-      if (r == k) L[r * LD + k] = piv;
-      else if (r > k) L[r * LD + k] = t / piv;
+  for (int oi = 0; oi < 16; ++oi) {
+    const int j = oq * 16 + oi;
+    if (q == oq) {
+      const float v = a[oi];
+      if (r == j) pivbuf[j & 1] = v;
+      colbuf[j & 1][r] = (r > j) ? v : 0.f;
     }
     __syncthreads();
+    const float d = pivbuf[j & 1];
+    if (tid == 0 && j < nb && !(d > 0.f) && info != nullptr) atomicCAS(info, 0, j0 + j + 1);
+    // 1/sqrt(d): MUFU.RSQ plus one Newton step (full fp32 accuracy at a third of the latency of
+    // sqrtf followed by a division -- this chain is on the critical path of every column)
+    const float dd = fmaxf(d, 1e-30f);
+    float rinv = rsqrtf(dd);
+    rinv = rinv * fmaf(-0.5f * dd, rinv * rinv, 1.5f);
+    const float piv = dd * rinv;
+    if (r == j) my_rinv = rinv;
+    const float lr = colbuf[j & 1][r] * rinv;            // L[r][j] (0 for r <= j)
+    const float s = lr * rinv;
+    const float4* cv = reinterpret_cast<const float4*>(&colbuf[j & 1][c0]);
+#pragma unroll
+    for (int v4 = 0; v4 < 4; ++v4) {
+      const float4 cc = cv[v4];
+      a[4 * v4 + 0] = fmaf(-s, cc.x, a[4 * v4 + 0]);
+      a[4 * v4 + 1] = fmaf(-s, cc.y, a[4 * v4 + 1]);
+      a[4 * v4 + 2] = fmaf(-s, cc.z, a[4 * v4 + 2]);
+      a[4 * v4 + 3] = fmaf(-s, cc.w, a[4 * v4 + 3]);
+    }
+    if (q == oq) a[oi] = (r > j) ? lr : (r == j ? piv : 0.f);
   }
-  // inverse by forward substitution: four threads per column c solve L x = e_c
-  const int c = tid >> 2;
-  // the columns of one warp have different trip counts: synchronise the 4-lane team only
-  const unsigned team = 0xFu << ((tid & 31) & ~3);
-  if (c < nb) {
-    for (int row = c; row < nb; ++row) {
-      float s = 0.f;
-      const float* lrow = L + row * LD;
-      float s1 = 0.f;
-      for (int base = c + q; base < row; base += 32) {
-        float a[8], x[8];
+  // a[] now holds row r of L (entries right of the diagonal are scratch)
+#pragma unroll 1
+  for (int oq = 0; oq < 4; ++oq)
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int k = base + 4 * u;
-          const bool ok = k < row;
-          a[u] = ok ? lrow[k] : 0.f;
-          x[u] = ok ? X[k * LD + c] : 0.f;
-        }
+  for (int oi = 0; oi < 16; ++oi) {
+    const int k = oq * 16 + oi;
+    const float lrk = __shfl_sync(0xffffffffu, a[oi], (lane & ~3) | oq);     // L[r][k]
+    if (r == k) {
+      const float dinv = my_rinv;
+      float4* rv = reinterpret_cast<float4*>(&rowbuf[k & 1][c0]);
 #pragma unroll
-        for (int u = 0; u < 8; u += 2) {
-          s = fmaf(-a[u], x[u], s);
-          s1 = fmaf(-a[u + 1], x[u + 1], s1);
-        }
+      for (int i = 0; i < 16; ++i) x[i] *= dinv;
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4)
+        rv[v4] = make_float4(x[4 * v4], x[4 * v4 + 1], x[4 * v4 + 2], x[4 * v4 + 3]);
+    }
+    __syncthreads();
+    if (r > k) {
+      const float4* rv = reinterpret_cast<const float4*>(&rowbuf[k & 1][c0]);
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4) {
+        const float4 xr = rv[v4];
+        x[4 * v4 + 0] = fmaf(-lrk, xr.x, x[4 * v4 + 0]);
+        x[4 * v4 + 1] = fmaf(-lrk, xr.y, x[4 * v4 + 1]);
+        x[4 * v4 + 2] = fmaf(-lrk, xr.z, x[4 * v4 + 2]);
+        x[4 * v4 + 3] = fmaf(-lrk, xr.w, x[4 * v4 + 3]);
       }
-      s += s1;
-      s += __shfl_xor_sync(team, s, 1);
-      s += __shfl_xor_sync(team, s, 2);
-      if (row == c) s += 1.f;
-      if (q == 0) X[row * LD + c] = s / lrow[row];
-      __syncwarp(team);
     }
   }
-  __syncthreads();
-  for (int i = tid; i < nb * nb; i += blockDim.x) {
-    const int rr = i / nb, cc = i % nb;
-    const float l = (cc <= rr) ? L[rr * LD + cc] : 0.f;
-    const float x = (cc <= rr) ? X[rr * LD + cc] : 0.f;
-    A[(int64_t)rr * lda + cc] = l;
-    Linv[rr * la::NB + cc] = x;
-    if (Linv_big != nullptr) Linv_big[(int64_t)rr * lda + cc] = x;
+  if (r < nb) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = c0 + i;
+      if (c >= nb) continue;
+      const float l = (c <= r) ? a[i] : 0.f;
+      const float xi = (c <= r) ? x[i] : 0.f;
+      A[(int64_t)r * lda + c] = l;
+      Linv[r * NB + c] = xi;
+      if (Linv_big != nullptr) Linv_big[(int64_t)r * lda + c] = xi;
+    }
   }
 }
 
@@ -275,8 +279,25 @@ struct LinalgWork {
   float* Linv;   // [K,K] -> L^-1 (lower)
   float* Dinv;   // [NB,NB] inverse of the current diagonal block
   float* T;      // [K,K] scratch for the block products of the triangular inverse
+  uint8_t* PA;   // fp16 planes of a GEMM operand (up to the full K x K matrix)
+  uint8_t* PB;   // fp16 planes of the second operand (up to half the matrix each way)
   int64_t bytes;
 };
+
+namespace la {
+constexpr int LEAF = 512;   // blocks up to this size are factored by the SIMT path
+inline int64_t first_half(int64_t n) { return ((n / 2 + 127) / 128) * 128; }
+// fp16 planes per operand of the tensor-core products.  Two (22 bits) are enough: measured against
+// an fp64 inverse the result is as accurate as with three (33 bits) -- the error that remains is
+// the factorisation's own -- at two thirds of the MMAs.  B200Q_INVERSE_PLANES=3 overrides (read once).
+inline int planes() {
+  static const int p = []() {
+    const char* e = std::getenv("B200Q_INVERSE_PLANES");
+    return (e != nullptr && e[0] == '3') ? 3 : 2;
+  }();
+  return p;
+}
+}  // namespace la
 
 static LinalgWork linalg_layout(void* work, int64_t K) {
   auto align = [](int64_t x) { return (x + 255) / 256 * 256; };
@@ -287,68 +308,116 @@ static LinalgWork linalg_layout(void* work, int64_t K) {
   w.Linv = reinterpret_cast<float*>(base + off); off += align(4 * K * K);
   w.Dinv = reinterpret_cast<float*>(base + off); off += align(4 * la::NB * la::NB);
   w.T = reinterpret_cast<float*>(base + off); off += align(4 * K * K);
+  w.PA = base + off; off += align(split_operand_bytes((int)K, (int)K));
+  const int half = (int)std::min<int64_t>(K, la::first_half(K) + 128);
+  w.PB = base + off; off += align(split_operand_bytes(half, half));
   w.bytes = off;
   return w;
 }
 
-// A (K x K, lower part valid) -> L in place (lower), Linv = L^-1 (lower, upper part zero).
-static int cholesky_and_inverse(cudaStream_t st, const LinalgWork& w, int64_t K, int* info) {
+// Leaf: the n x n diagonal block at (a0, a0) of A (row stride ld) -> L in place and L^-1 into
+// Linv, everything on the FP32 pipe.  Right-looking over 64-column steps; the triangular inverse
+// of the block by divide and conquer with batched GEMMs.
+static void leaf_factor_inv(cudaStream_t st, const LinalgWork& w, int64_t ld, int64_t a0, int64_t n,
+                            int* info) {
   using namespace la;
-  const int diag_smem = 2 * NB * (NB + 4) * (int)sizeof(float);
-  cudaFuncSetAttribute(potrf_inv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem);
-  cudaMemsetAsync(w.Linv, 0, sizeof(float) * K * K, st);
-  {
-    KernelScope scope("inv_potrf", 0, (double)K * K * K / 3.0, st);
-    for (int64_t j = 0; j < K; j += NB) {
-      const int nb = (int)std::min<int64_t>(NB, K - j);
-      float* Ajj = w.A + j * K + j;
-      // factor the diagonal block; its inverse goes to Dinv (dense copy for the panel GEMM) and
-      // straight into the diagonal block of L^-1
-      {
-        KernelScope diag_scope("inv_diag", 0, 0, st);
-        potrf_inv_diag_kernel<<<1, 4 * NB, diag_smem, st>>>(Ajj, K, nb, w.Dinv, w.Linv + j * K + j, info,
-                                                         (int)j);
-      }
-      count_launch();
-      const int rem = (int)(K - j - nb);
-      if (rem > 0) {
-        float* A21 = w.A + (j + nb) * K + j;
-        // L21 = A21 * L11^-T, in place: the panel is one column tile wide (nb <= BN), so each CTA
-        // reads exactly the rows it later overwrites
-        sgemm<false, true>(st, rem, nb, nb, 1.f, A21, K, w.Dinv, NB, 0.f, A21, K);
-        // A22 -= L21 L21^T (lower tiles)
-        float* A22 = w.A + (j + nb) * K + (j + nb);
-        sgemm<false, true>(st, rem, rem, nb, -1.f, A21, K, A21, K, 1.f, A22, K, /*tri=*/1);
-      }
+  float* Ab = w.A + a0 * ld + a0;
+  float* Mb = w.Linv + a0 * ld + a0;
+  float* Tb = w.T + a0 * ld + a0;
+  for (int64_t j = 0; j < n; j += NB) {
+    const int nb = (int)std::min<int64_t>(NB, n - j);
+    float* Ajj = Ab + j * ld + j;
+    {
+      KernelScope diag_scope("inv_diag", 0, 0, st);
+      potrf_inv_diag_kernel<<<1, 4 * NB, 0, st>>>(Ajj, ld, nb, w.Dinv, Mb + j * ld + j, info,
+                                                  (int)(a0 + j));
+    }
+    count_launch();
+    const int rem = (int)(n - j - nb);
+    if (rem > 0) {
+      float* A21 = Ab + (j + nb) * ld + j;
+      // L21 = A21 * L11^-T, in place: the panel is one column tile wide (nb <= BN), so each CTA
+      // reads exactly the rows it later overwrites
+      sgemm<false, true>(st, rem, nb, nb, 1.f, A21, ld, w.Dinv, NB, 0.f, A21, ld);
+      // A22 -= L21 L21^T (lower tiles)
+      float* A22 = Ab + (j + nb) * ld + (j + nb);
+      sgemm<false, true>(st, rem, rem, nb, -1.f, A21, ld, A21, ld, 1.f, A22, ld, /*tri=*/1);
     }
   }
   // L^-1 by divide and conquer over the block diagonal: with M11, M22 the inverses of two adjacent
   // s x s diagonal blocks and L21 the block below the first,  M21 = -M22 * (L21 * M11).
-  // Level s handles all K/(2s) pairs at once (batched launch, operands advance by 2s*(K+1)); the
-  // last pair of a level may be ragged.  Every level is two GEMMs with full 2-D parallelism, where
-  // a row- or column-sweep exposes only K/128 CTAs.
-  {
-    KernelScope scope("inv_trtri", 0, (double)K * K * K / 3.0, st);
-    for (int64_t s = NB; s < K; s *= 2) {
-      const int64_t full = K / (2 * s);                       // pairs with two complete blocks
-      const int64_t stride = 2 * s * (K + 1);
-      auto level = [&](int64_t a, int64_t s2, int batch) {
-        const float* L21 = w.A + (a + s) * K + a;
-        float* S21 = w.T + (a + s) * K + a;
-        float* M21 = w.Linv + (a + s) * K + a;
-        // S21 = L21 * M11          (M11 lower triangular: k starts at the column tile)
-        sgemm<false, false>(st, (int)s2, (int)s, (int)s, 1.f, L21, K, w.Linv + a * K + a, K, 0.f, S21,
-                            K, /*tri=*/3, batch, stride);
-        // M21 = -M22 * S21         (M22 lower triangular: k stops at the row tile)
-        sgemm<false, false>(st, (int)s2, (int)s, (int)s2, -1.f, w.Linv + (a + s) * K + (a + s), K, S21,
-                            K, 0.f, M21, K, /*tri=*/4, batch, stride);
-      };
-      if (full > 0) level(0, s, (int)full);
-      const int64_t a = full * 2 * s;                         // ragged tail: second block is short
-      const int64_t s2 = K - a - s;
-      if (s2 > 0) level(a, s2, 1);
-    }
+  // Level s handles all n/(2s) pairs at once (batched launch, operands advance by 2s*(ld+1)); the
+  // last pair of a level may be ragged.
+  for (int64_t s = NB; s < n; s *= 2) {
+    const int64_t full = n / (2 * s);                       // pairs with two complete blocks
+    const int64_t stride = 2 * s * (ld + 1);
+    auto level = [&](int64_t a, int64_t s2, int batch) {
+      const float* L21 = Ab + (a + s) * ld + a;
+      float* S21 = Tb + (a + s) * ld + a;
+      float* M21 = Mb + (a + s) * ld + a;
+      // S21 = L21 * M11          (M11 lower triangular: k starts at the column tile)
+      sgemm<false, false>(st, (int)s2, (int)s, (int)s, 1.f, L21, ld, Mb + a * ld + a, ld, 0.f, S21,
+                          ld, /*tri=*/3, batch, stride);
+      // M21 = -M22 * S21         (M22 lower triangular: k stops at the row tile)
+      sgemm<false, false>(st, (int)s2, (int)s, (int)s2, -1.f, Mb + (a + s) * ld + (a + s), ld, S21,
+                          ld, 0.f, M21, ld, /*tri=*/4, batch, stride);
+    };
+    if (full > 0) level(0, s, (int)full);
+    const int64_t a = full * 2 * s;                         // ragged tail: second block is short
+    const int64_t s2 = n - a - s;
+    if (s2 > 0) level(a, s2, 1);
   }
+}
+
+// Recursive blocked factor-and-invert of the n x n diagonal block at (a0, a0):
+//     A = [A11 . ; A21 A22]   ->   L11, M11 = L11^-1        (recursion)
+//                                  L21 = A21 M11^T           (GEMM; M11 triangular: half the k range)
+//                                  A22 -= L21 L21^T          (GEMM, lower tiles)
+//                                  L22, M22                  (recursion)
+//                                  M21 = -M22 (L21 M11)      (two GEMMs, triangular k ranges)
+// so that nearly all of the K^3 work sits in a few large products, which run on the tensor cores
+// (splitgemm.cu); only blocks of <= LEAF columns use the FP32 pipe.
+static int factor_inv(cudaStream_t st, const LinalgWork& w, int64_t K, int64_t a0, int64_t n,
+                      int* info) {
+  if (n <= la::LEAF) {
+    leaf_factor_inv(st, w, K, a0, n, info);
+    return B200Q_OK;
+  }
+  const int64_t n1 = la::first_half(n), n2 = n - n1;
+  int rc = factor_inv(st, w, K, a0, n1, info);
+  if (rc != B200Q_OK) return rc;
+  float* A21 = w.A + (a0 + n1) * K + a0;
+  float* A22 = w.A + (a0 + n1) * K + (a0 + n1);
+  const float* M11 = w.Linv + a0 * K + a0;
+  const float* M22 = w.Linv + (a0 + n1) * K + (a0 + n1);
+  float* M21 = w.Linv + (a0 + n1) * K + a0;
+  float* S21 = w.T + (a0 + n1) * K + a0;
+  SplitOperand a, b;
+#define LA_TRY(x) do { rc = (x); if (rc != B200Q_OK) return rc; } while (0)
+  LA_TRY(split_operand(st, A21, K, (int)n2, (int)n1, false, la::planes(), w.PA, &a));
+  LA_TRY(split_operand(st, M11, K, (int)n1, (int)n1, false, la::planes(), w.PB, &b));
+  LA_TRY(split_gemm(st, a, b, 1.f, 0.f, A21, K, SG_KE_N));              // L21 = A21 M11^T
+  LA_TRY(split_operand(st, A21, K, (int)n2, (int)n1, false, la::planes(), w.PA, &a));
+  LA_TRY(split_gemm(st, a, a, -1.f, 1.f, A22, K, SG_LOWER));            // A22 -= L21 L21^T
+  LA_TRY(factor_inv(st, w, K, a0 + n1, n2, info));
+  LA_TRY(split_operand(st, A21, K, (int)n2, (int)n1, false, la::planes(), w.PA, &a));  // the recursion reused PA
+  LA_TRY(split_operand(st, M11, K, (int)n1, (int)n1, true, la::planes(), w.PB, &b));   // B[n][k] = M11[k][n]
+  LA_TRY(split_gemm(st, a, b, 1.f, 0.f, S21, K, SG_KB_N));              // S = L21 M11
+  LA_TRY(split_operand(st, M22, K, (int)n2, (int)n2, false, la::planes(), w.PA, &a));
+  LA_TRY(split_operand(st, S21, K, (int)n2, (int)n1, true, la::planes(), w.PB, &b));   // B[n][k] = S[k][n]
+  LA_TRY(split_gemm(st, a, b, -1.f, 0.f, M21, K, SG_KE_M));             // M21 = -M22 S
+  return B200Q_OK;
+}
+
+// A (K x K, lower part valid) -> L in place (lower), Linv = L^-1 (lower, upper part zero).
+static int cholesky_and_inverse(cudaStream_t st, const LinalgWork& w, int64_t K, int* info) {
+  cudaMemsetAsync(w.Linv, 0, sizeof(float) * K * K, st);
+  int rc;
+  {
+    KernelScope scope("inv_factor", 0, 2.0 * (double)K * K * K / 3.0, st);
+    rc = factor_inv(st, w, K, 0, K, info);
+  }
+  if (rc != B200Q_OK) return rc;
   return check_launch("cholesky_and_inverse");
 }
 
@@ -496,8 +565,14 @@ int b200q_spd_inverse(const float* H, float* Hinv, float* U, int64_t K, void* wo
     rc = cholesky_and_inverse(st, w, K, info);
     if (rc != B200Q_OK) return rc;
     // H^-1 = L^-T L^-1
-    sgemm<true, false>(st, (int)K, (int)K, (int)K, 1.f, w.Linv, K, w.Linv, K, 0.f, Hinv, K,
-                       /*tri=*/2);
+    {
+      KernelScope product_scope("inv_product", 0, (double)K * K * K / 3.0, st);
+      SplitOperand mt;                                    // A[m][k] = B[m][k] = Linv[k][m]
+      rc = split_operand(st, w.Linv, K, (int)K, (int)K, true, la::planes(), w.PA, &mt);
+      if (rc != B200Q_OK) return rc;
+      rc = split_gemm(st, mt, mt, 1.f, 0.f, Hinv, K, SG_KB_M | SG_KB_N | SG_SYMM);
+      if (rc != B200Q_OK) return rc;
+    }
     rc = check_launch("spd_inverse/product");
     if (rc != B200Q_OK) return rc;
   }

@@ -374,23 +374,28 @@ static int make_tmap_2d_16bit(CUtensorMap* map, const void* base, int64_t rows, 
   return B200Q_OK;
 }
 
-static int hessian_splits(int64_t K, int64_t T) {
-  // only tiles that touch the upper triangle run (see the kernel)
+// How many token splits per output tile.  One CTA per (tile, split), one CTA per SM at a time, so
+// the launch takes ceil(tiles * s / 148) rounds of (k-blocks per split) MMA stages plus an
+// epilogue that writes the fp32 tile and its mirror image to HBM; s > 1 adds the pass that sums
+// the partial matrices.  `straight` = the single-split result can go to H directly (no such pass).
+// Constants are measured B200 figures (0.44 us per 128x256x64 stage under the sustained power
+// limit, ~6.5 us for 148 concurrent tile epilogues, 6.2 TB/s for the reduction).
+static int hessian_splits(int64_t K, int64_t T, bool straight) {
   const int64_t tm = (K + hg::BM - 1) / hg::BM, tn = (K + hg::BN - 1) / hg::BN;
-  int64_t tiles = 0;
+  int64_t tiles = 0;                       // only tiles that touch the upper triangle run
   for (int64_t m = 0; m < tm; ++m)
     for (int64_t n = 0; n < tn; ++n)
       if ((n + 1) * hg::BN > m * hg::BM) ++tiles;
   const int64_t kblocks = (T + hg::BKT - 1) / hg::BKT;
-  // one CTA per (tile, split), one CTA per SM at a time: pick the split count (<= 16, >= 8
-  // k-blocks of work each) whose CTA count fills whole waves of 148 best; ties go to fewer splits
   const int64_t max_s = std::max<int64_t>(1, std::min<int64_t>(16, kblocks / 8));
   int64_t best = 1;
-  double best_eff = -1.0;
+  double best_us = 1e30;
   for (int64_t s = 1; s <= max_s; ++s) {
-    const int64_t ctas = tiles * s;
-    const double eff = (double)ctas / (double)(((ctas + kNumSMs - 1) / kNumSMs) * kNumSMs);
-    if (eff > best_eff + 0.01) { best_eff = eff; best = s; }
+    const double rounds = (double)((tiles * s + kNumSMs - 1) / kNumSMs);
+    const double kb = (double)((kblocks + s - 1) / s);
+    double us = rounds * (kb * 0.44 + 6.5);
+    if (s > 1 || !straight) us += (double)(s + 1) * (double)K * (double)K * 4.0 / 6.2e6;
+    if (us < best_us * 0.995) { best_us = us; best = s; }
   }
   return (int)best;
 }
@@ -404,10 +409,12 @@ struct HessianWork {
   int64_t bytes;
 };
 
-static HessianWork hessian_layout(void* work, int64_t T, int64_t K, int n_samples) {
+static HessianWork hessian_layout(void* work, int64_t T, int64_t K, int n_samples,
+                                  int straight /* 0, 1, or -1 = size for either */) {
   HessianWork w;
   w.chunks = (int)std::max<int64_t>(1, std::min<int64_t>(64, (2 * kNumSMs) / std::max(1, n_samples)));
-  w.splits = hessian_splits(K, T);
+  w.splits = straight < 0 ? std::max(hessian_splits(K, T, false), hessian_splits(K, T, true))
+                          : hessian_splits(K, T, straight != 0);
   auto align = [](int64_t x) { return (x + 255) / 256 * 256; };
   int64_t off = 0;
   uint8_t* base = static_cast<uint8_t*>(work);
@@ -562,25 +569,62 @@ awq_loss_gemm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_co
 // can use this triangular operand and skip the k-blocks right of each output tile.
 __global__ void __launch_bounds__(256)
 h_to_lower_bf16_kernel(const float* __restrict__ H, __nv_bfloat16* __restrict__ Hb, int64_t K) {
-  __shared__ float tile[32][33];
-  const int64_t n0 = (int64_t)blockIdx.y * 32, k0 = (int64_t)blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
-  if (k0 > n0 + 31) {                                            // entirely above the diagonal
-    for (int r = ty; r < 32; r += 8)
-      if (n0 + r < K && k0 + tx < K) Hb[(n0 + r) * K + k0 + tx] = __float2bfloat16_rn(0.f);
+  constexpr int TS = 64;                                        // 64 x 64 block per CTA
+  __shared__ float tr[TS][TS + 1];
+  const int64_t n0 = (int64_t)blockIdx.y * TS, k0 = (int64_t)blockIdx.x * TS;
+  const int c4 = (threadIdx.x & 15) * 4, r0 = threadIdx.x >> 4;  // 16 float4 per row, 16 rows / pass
+  const bool vec = (K % 4 == 0);
+  if (k0 >= n0 + TS) {                                          // entirely above the diagonal
+    for (int r = r0; r < TS; r += 16) {
+      const int64_t n = n0 + r;
+      if (n >= K) break;
+      for (int j = 0; j < 4; ++j)
+        if (k0 + c4 + j < K) Hb[n * K + k0 + c4 + j] = __float2bfloat16_rn(0.f);
+    }
     return;
   }
-  // transposed block H[k0.., n0..] through shared memory (coalesced both ways)
-  for (int r = ty; r < 32; r += 8)
-    tile[r][tx] = (k0 + r < K && n0 + tx < K) ? H[(k0 + r) * K + n0 + tx] : 0.f;
+  // block H[k0.., n0..] into shared memory (coalesced 16-byte loads), read back transposed
+  for (int r = r0; r < TS; r += 16) {
+    const int64_t kr = k0 + r, nc = n0 + c4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kr < K) {
+      if (vec && nc + 3 < K) v = *reinterpret_cast<const float4*>(H + kr * K + nc);
+      else {
+        if (nc < K) v.x = H[kr * K + nc];
+        if (nc + 1 < K) v.y = H[kr * K + nc + 1];
+        if (nc + 2 < K) v.z = H[kr * K + nc + 2];
+        if (nc + 3 < K) v.w = H[kr * K + nc + 3];
+      }
+    }
+    tr[r][c4] = v.x; tr[r][c4 + 1] = v.y; tr[r][c4 + 2] = v.z; tr[r][c4 + 3] = v.w;
+  }
   __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int64_t n = n0 + r, k = k0 + tx;
-    if (n >= K || k >= K) continue;
-    float v = 0.f;
-    if (k < n) v = H[n * K + k] + tile[tx][r];
-    else if (k == n) v = H[n * K + k];
-    Hb[n * K + k] = __float2bfloat16_rn(v);
+  for (int r = r0; r < TS; r += 16) {
+    const int64_t n = n0 + r;
+    if (n >= K) break;
+    float h[4] = {0.f, 0.f, 0.f, 0.f};
+    const int64_t kc = k0 + c4;
+    if (vec && kc + 3 < K) {
+      const float4 v = *reinterpret_cast<const float4*>(H + n * K + kc);
+      h[0] = v.x; h[1] = v.y; h[2] = v.z; h[3] = v.w;
+    } else {
+      for (int j = 0; j < 4; ++j) if (kc + j < K) h[j] = H[n * K + kc + j];
+    }
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t k = kc + j;
+      o[j] = (k < n) ? h[j] + tr[c4 + j][r] : (k == n ? h[j] : 0.f);
+    }
+    if (vec && kc + 3 < K) {
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&p0);
+      pk.y = *reinterpret_cast<const uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(Hb + n * K + kc) = pk;
+    } else {
+      for (int j = 0; j < 4; ++j) if (kc + j < K) Hb[n * K + kc + j] = __float2bfloat16_rn(o[j]);
+    }
   }
 }
 
@@ -648,7 +692,7 @@ extern "C" {
 
 int64_t b200q_hessian_workspace(int64_t T, int64_t K, int n_samples) {
   if (T <= 0 || K <= 0 || n_samples <= 0) return 0;
-  return hessian_layout(nullptr, T, K, n_samples).bytes;
+  return hessian_layout(nullptr, T, K, n_samples, -1).bytes;
 }
 
 int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, int64_t K, int dtype,
@@ -661,7 +705,6 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t T = (int64_t)n_samples * rows_per_sample;
   B200Q_REQUIRE(T < (1ll << 31) && K < (1ll << 31), "hessian_accum: dimension too large");
-  HessianWork w = hessian_layout(work, T, K, n_samples);
   const double flops = 2.0 * (double)T * (double)K * (double)K;
 
   // A plain Gram matrix (no per-sample normalisation, no norms wanted) of 16-bit activations needs
@@ -669,6 +712,7 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
   // caller's tensor directly.  Everything else goes through stats + prescale into fp16.
   const bool direct = !normalize && norms_out == nullptr && (dtype == B200Q_F16 || dtype == B200Q_BF16);
   const bool bf16_ops = direct && dtype == B200Q_BF16;
+  HessianWork w = hessian_layout(work, T, K, n_samples, (direct && !accumulate) ? 1 : 0);
   if (!direct) {
     KernelScope scope("hessian_prescale", 3.0 * T * K * elem_size(dtype), 0, st);
     B200Q_DISPATCH_DTYPE(dtype, Tt, {
@@ -705,22 +749,25 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
   const int64_t kblocks = (T + hg::BKT - 1) / hg::BKT;
   const int64_t kb_per_split = (kblocks + w.splits - 1) / w.splits;
   const int64_t tokens_per_split = kb_per_split * hg::BKT;
+  // one split, nothing to add to and no scale to undo: the tiles go straight into H
+  const bool straight = direct && w.splits == 1 && !accumulate;
+  float* gemm_out = straight ? H : w.partial;
   {
     KernelScope scope("hessian_gemm", 0, flops, st);
     const int tiles_n = (int)((K + hg::BN - 1) / hg::BN);
     const int tiles_m = (int)((K + hg::BM - 1) / hg::BM);
     dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)w.splits);
     if (bf16_ops)
-      hessian_gemm_kernel<true><<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(tmap, w.partial, K, T,
+      hessian_gemm_kernel<true><<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(tmap, gemm_out, K, T,
                                                                            tokens_per_split, tiles_n);
     else
-      hessian_gemm_kernel<false><<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(tmap, w.partial, K, T,
+      hessian_gemm_kernel<false><<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(tmap, gemm_out, K, T,
                                                                             tokens_per_split, tiles_n);
     count_launch();
     rc = check_launch("hessian_gemm");
     if (rc != B200Q_OK) return rc;
   }
-  {
+  if (!straight) {
     KernelScope scope("hessian_reduce", sizeof(float) * (double)(w.splits + 1) * K * K, 0, st);
     const int64_t KK = K * K;
     const int blocks = (int)std::min<int64_t>((KK / 4 + 255) / 256, (int64_t)kNumSMs * 16);
@@ -768,7 +815,10 @@ int b200q_awq_search_loss(const void* W, int64_t N, int64_t K, int64_t group, in
       cudaMemsetAsync(w.D, 0, 2 * Mtot * K, st);
     rc = launch_awq_delta(W, w.D, salient, N, K, w.rows_pad * K, n_bit, sf_host, n_cand, dtype, st);
     if (rc != B200Q_OK) return rc;
-    const unsigned tb = (unsigned)((K + 31) / 32);
+  }
+  {
+    KernelScope scope("awq_search_fold", 7.0 * K * K, 0, st);   // lower half: 8 B in + 2 B out; upper: 2 B out
+    const unsigned tb = (unsigned)((K + 63) / 64);
     h_to_lower_bf16_kernel<<<dim3(tb, tb), 256, 0, st>>>(H, w.Hb, K);
     count_launch();
   }

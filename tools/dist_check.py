@@ -71,6 +71,22 @@ with torch.no_grad():
     full = nn.Sequential(nn.Linear(K, N, bias=False)).to(dev); full[0].weight.data = W.clone().to(dev)
     results[f"awq search argmin sharded == unsharded ({best})"] = \
         best == awq_quantizer.awq_search_scale_factor(full, 4, 128, {"0": acts}, n_grid=10)
+    # three layers with different K: exercises the look-ahead (next layer's Gram matrix and its
+    # all-reduce are started before the current layer's search) with raw 3-D activations
+    Ks = [256, 512, 384]
+    gg = torch.Generator().manual_seed(5)
+    Ws = [torch.randn(512, k, generator=gg) * 0.02 for k in Ks]
+    acts3 = {str(i): (torch.randn(4, 128, k, generator=gg)).to(torch.bfloat16).to(dev) for i, k in enumerate(Ks)}
+    q0, q1 = D.shard_rows(512, world, rank)
+    def stack(rows):
+        net = nn.Sequential(*[nn.Linear(k, 1, bias=False) for k in Ks]).to(dev)
+        for lin, w in zip(net, Ws):
+            lin.weight.data = w[rows].clone().to(dev)
+        return net
+    with D.row_sharded():
+        b_sh = awq_quantizer.awq_search_scale_factor(stack(slice(q0, q1)), 4, 128, acts3, n_grid=10)
+    b_full = awq_quantizer.awq_search_scale_factor(stack(slice(0, 512)), 4, 128, acts3, n_grid=10)
+    results[f"3-layer awq search with look-ahead: sharded {b_sh} == unsharded {b_full}"] = b_sh == b_full
 if rank == 0:
     for k, v in results.items():
         print(("PASS " if v else "FAIL ") + k)
