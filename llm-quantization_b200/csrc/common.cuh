@@ -21,6 +21,11 @@ void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 void count_launch(int n = 1);
 int check_launch(const char* what);
+int64_t launches_so_far();
+// While a thread records launches into a CUDA graph (linalg.cu) the event profiler stays out of the
+// way: events recorded during capture would become graph nodes.
+void set_stream_capture(bool on);
+bool in_stream_capture();
 
 // Brackets the launches of one C-ABI call with CUDA events when profiling is on (core.cu).
 class KernelScope {

@@ -18,6 +18,10 @@ int fail(int code, const std::string& msg) {
   return code;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int64_t launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
+static thread_local bool t_capture = false;
+void set_stream_capture(bool on) { t_capture = on; }
+bool in_stream_capture() { return t_capture; }
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -41,7 +45,7 @@ static std::vector<ProfRec> g_prof;
 
 KernelScope::KernelScope(const char* name, double bytes, double flops, cudaStream_t st)
     : name_(name), bytes_(bytes), flops_(flops), st_(st), e0_(nullptr), e1_(nullptr) {
-  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  if (!g_prof_on.load(std::memory_order_relaxed) || t_capture) return;
   if (cudaEventCreate(&e0_) != cudaSuccess || cudaEventCreate(&e1_) != cudaSuccess) {
     e0_ = e1_ = nullptr;
     cudaGetLastError();

@@ -16,6 +16,10 @@
 // H^-1 = R^-T R^-1 and U = R^-1 = J Lr^-1 J: the same factor-and-invert on the reversed matrix.
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
 
 #include "common.cuh"
 #include "splitgemm.cuh"
@@ -281,6 +285,7 @@ struct LinalgWork {
   float* T;      // [K,K] scratch for the block products of the triangular inverse
   uint8_t* PA;   // fp16 planes of a GEMM operand (up to the full K x K matrix)
   uint8_t* PB;   // fp16 planes of the second operand (up to half the matrix each way)
+  int* info;     // first non-positive pivot seen by the diagonal kernels (0 = none)
   int64_t bytes;
 };
 
@@ -311,6 +316,7 @@ static LinalgWork linalg_layout(void* work, int64_t K) {
   w.PA = base + off; off += align(split_operand_bytes((int)K, (int)K));
   const int half = (int)std::min<int64_t>(K, la::first_half(K) + 128);
   w.PB = base + off; off += align(split_operand_bytes(half, half));
+  w.info = reinterpret_cast<int*>(base + off); off += 256;
   w.bytes = off;
   return w;
 }
@@ -409,15 +415,90 @@ static int factor_inv(cudaStream_t st, const LinalgWork& w, int64_t K, int64_t a
   return B200Q_OK;
 }
 
+__global__ void merge_info_kernel(const int* __restrict__ src, int* __restrict__ dst) {
+  if (*src != 0) atomicCAS(dst, 0, *src);
+}
+
+// The factorisation of one matrix is ~500 small dependent launches (64-column diagonal kernels,
+// leaf GEMMs, operand splits) whose host-side cost -- launch calls and tensor-map encodes -- would
+// leave the GPU waiting.  The sequence only depends on K and on the workspace address, so it is
+// recorded ONCE into a CUDA graph (captured on a private stream: the caller's may be the legacy
+// default stream, which cannot be captured) and replayed with a single launch afterwards.
+// B200Q_INVERSE_GRAPH=0 keeps the direct launches (per-stage profiling scopes need them).
+struct FactorGraph {
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;
+};
+static std::mutex g_graph_mu;
+static std::map<std::tuple<int, const void*, int64_t>, FactorGraph> g_graphs;
+
+static bool graphs_enabled() {
+  static const bool on = []() {
+    const char* e = std::getenv("B200Q_INVERSE_GRAPH");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+
+static int factor_direct(cudaStream_t st, const LinalgWork& w, int64_t K) {
+  cudaMemsetAsync(w.Linv, 0, sizeof(float) * K * K, st);
+  cudaMemsetAsync(w.info, 0, sizeof(int), st);
+  int rc = factor_inv(st, w, K, 0, K, w.info);
+  if (rc != B200Q_OK) return rc;
+  return check_launch("cholesky_and_inverse");
+}
+
 // A (K x K, lower part valid) -> L in place (lower), Linv = L^-1 (lower, upper part zero).
 static int cholesky_and_inverse(cudaStream_t st, const LinalgWork& w, int64_t K, int* info) {
-  cudaMemsetAsync(w.Linv, 0, sizeof(float) * K * K, st);
-  int rc;
-  {
-    KernelScope scope("inv_factor", 0, 2.0 * (double)K * K * K / 3.0, st);
-    rc = factor_inv(st, w, K, 0, K, info);
+  KernelScope scope("inv_factor", 0, 2.0 * (double)K * K * K / 3.0, st);
+  int rc = B200Q_OK;
+  if (!graphs_enabled()) {
+    rc = factor_direct(st, w, K);
+  } else {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_graph_mu);
+    const auto key = std::make_tuple(dev, static_cast<const void*>(w.A), K);
+    auto it = g_graphs.find(key);
+    if (it == g_graphs.end()) {
+      if (g_graphs.size() >= 32) {               // workspaces come and go: do not hoard graphs
+        for (auto& kv : g_graphs) cudaGraphExecDestroy(kv.second.exec);
+        g_graphs.clear();
+      }
+      rc = split_gemm_prepare();                 // function attributes: not during capture
+      if (rc != B200Q_OK) return rc;
+      cudaStream_t cap = nullptr;
+      if (cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(B200Q_ECUDA, "spd_inverse: cannot create the capture stream");
+      FactorGraph fg;
+      cudaGraph_t graph = nullptr;
+      const int64_t before = launches_so_far();
+      set_stream_capture(true);
+      cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+      if (e == cudaSuccess) {
+        rc = factor_direct(cap, w, K);
+        e = cudaStreamEndCapture(cap, &graph);
+      }
+      set_stream_capture(false);
+      fg.launches = launches_so_far() - before;
+      count_launch((int)-fg.launches);           // nothing has run yet; replays are counted below
+      if (e == cudaSuccess && rc == B200Q_OK) e = cudaGraphInstantiate(&fg.exec, graph, 0);
+      if (graph != nullptr) cudaGraphDestroy(graph);
+      cudaStreamDestroy(cap);
+      if (rc != B200Q_OK) return rc;
+      if (e != cudaSuccess)
+        return fail(B200Q_ECUDA, std::string("spd_inverse: graph capture: ") + cudaGetErrorString(e));
+      it = g_graphs.emplace(key, fg).first;
+    }
+    if (cudaGraphLaunch(it->second.exec, st) != cudaSuccess)
+      return fail(B200Q_ECUDA, "spd_inverse: graph launch failed");
+    count_launch((int)it->second.launches);
   }
   if (rc != B200Q_OK) return rc;
+  if (info != nullptr) {
+    merge_info_kernel<<<1, 1, 0, st>>>(w.info, info);
+    count_launch();
+  }
   return check_launch("cholesky_and_inverse");
 }
 

@@ -369,6 +369,14 @@ int split_operand(cudaStream_t st, const float* src, int64_t ld, int src_rows, i
   return check_launch("split_operand");
 }
 
+int split_gemm_prepare() {
+  // (per-device attribute; the call is cheap and idempotent)
+  if (cudaFuncSetAttribute(split_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           sg::SMEM_BYTES) != cudaSuccess)
+    return fail(B200Q_ECUDA, "split_gemm: cannot raise shared memory");
+  return B200Q_OK;
+}
+
 int split_gemm(cudaStream_t st, const SplitOperand& A, const SplitOperand& B, float alpha, float beta,
                float* C, int64_t ldc, int flags) {
   const int M = A.rows, N = B.rows, Kd = A.cols;
@@ -381,9 +389,7 @@ int split_gemm(cudaStream_t st, const SplitOperand& A, const SplitOperand& B, fl
     if ((rc = plane_map(&ma[i], A.p[i], M, Kd, A.ld16, sg::BM)) != B200Q_OK) return rc;
     if ((rc = plane_map(&mb[i], B.p[i], N, Kd, B.ld16, sg::BN)) != B200Q_OK) return rc;
   }
-  if (cudaFuncSetAttribute(split_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           sg::SMEM_BYTES) != cudaSuccess)
-    return fail(B200Q_ECUDA, "split_gemm: cannot raise shared memory");
+  if (!in_stream_capture() && (rc = split_gemm_prepare()) != B200Q_OK) return rc;
   dim3 grid((unsigned)((N + sg::BN - 1) / sg::BN), (unsigned)((M + sg::BM - 1) / sg::BM));
   KernelScope scope("inv_gemm", 0, 2.0 * M * (double)N * Kd, st);   // dense count; tri flags skip part
   split_gemm_kernel<<<grid, sg::THREADS, sg::SMEM_BYTES, st>>>(

@@ -36,6 +36,9 @@ int64_t split_operand_bytes(int rows, int cols);
 int split_operand(cudaStream_t st, const float* src, int64_t ld, int src_rows, int src_cols,
                   bool transpose, int planes, void* buf, SplitOperand* out);
 
+// One-time function attributes of the GEMM kernel (call before recording launches into a graph).
+int split_gemm_prepare();
+
 // C[M, N] = alpha * A B^T + beta * C   (M = A.rows, N = B.rows, inner = A.cols = B.cols)
 int split_gemm(cudaStream_t st, const SplitOperand& A, const SplitOperand& B, float alpha, float beta,
                float* C, int64_t ldc, int flags);
