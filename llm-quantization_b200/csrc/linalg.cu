@@ -672,7 +672,9 @@ int b200q_spd_inverse(const float* H, float* Hinv, float* U, int64_t K, void* wo
 
 int64_t b200q_gptq_compensated_workspace(int64_t N, int64_t K) {
   if (N <= 0 || K <= 0) return 0;
-  return (int64_t)sizeof(float) * (N * gc::B + 2 * N) + 512;
+  auto align = [](int64_t x) { return (x + 255) / 256 * 256; };
+  return align((int64_t)sizeof(float) * (N * gc::B + 2 * N)) + align(split_operand_bytes((int)N, gc::B)) +
+         align(split_operand_bytes((int)K, (int)K)) + 512;
 }
 
 // W (fp32 [N,K], destroyed) -> Q (fp32 [N,K]) with U = upper Cholesky factor of H^-1.
@@ -689,14 +691,24 @@ int b200q_gptq_compensated(float* W, float* Q, const float* U, int64_t N, int64_
   B200Q_REQUIRE(K % G == 0 || G >= K, "gptq_compensated: in_features not divisible by group size");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   KernelScope scope("gptq_compensated", 2.0 * N * K * 4, (double)N * K * K, st);
+  B200Q_REQUIRE(N < (1 << 30) && K < (1 << 30), "gptq_compensated: dimension too large");
+  auto align = [](int64_t x) { return (x + 255) / 256 * 256; };
+  B200Q_REQUIRE((reinterpret_cast<uintptr_t>(work) & 255u) == 0, "gptq_compensated: workspace not 256-byte aligned");
   float* Err = static_cast<float*>(work);
   float* scales = Err + N * gc::B;
   float* zeros = scales + N;
+  uint8_t* planes_err = static_cast<uint8_t*>(work) + align((int64_t)sizeof(float) * (N * gc::B + 2 * N));
+  uint8_t* planes_u = planes_err + align(split_operand_bytes((int)N, gc::B));
   const float maxint = (float)((1 << n_bit) - 1);
   const int smem = gc::B * (gc::B + 1) * (int)sizeof(float);
   cudaFuncSetAttribute(gptq_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(gptq_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int blocks = (int)std::min<int64_t>((N + 7) / 8, (int64_t)kNumSMs * 2);
+  // U^T as tensor-core planes, once: the lazy update of block c0 multiplies by U[c0:c1, c1:], whose
+  // transpose is the sub-block [c1:, c0:c1] of these planes
+  SplitOperand ut;
+  int rc = split_operand(st, U, K, (int)K, (int)K, true, 2, planes_u, &ut);
+  if (rc != B200Q_OK) return rc;
   for (int64_t c0 = 0; c0 < K; c0 += gc::B) {
     const int nb = (int)std::min<int64_t>(gc::B, K - c0);
     if (G == gc::B) {
@@ -713,9 +725,14 @@ int b200q_gptq_compensated(float* W, float* Q, const float* U, int64_t N, int64_
     count_launch();
     const int64_t rest = K - (c0 + nb);
     if (rest > 0) {
-      // W[:, c1:] -= Err[N, nb] * U[c0:c1, c1:]          (lazy rank-128 update)
-      sgemm<false, false>(st, (int)N, (int)rest, nb, -1.f, Err, gc::B, U + c0 * K + (c0 + nb), K, 1.f,
-                          W + (c0 + nb), K);
+      // W[:, c1:] -= Err[N, nb] * U[c0:c1, c1:]    (lazy rank-128 update, on the tensor cores:
+      // fp32 operands split into fp16 planes, splitgemm.cu)
+      SplitOperand e;
+      rc = split_operand(st, Err, gc::B, (int)N, nb, false, 2, planes_err, &e);
+      if (rc != B200Q_OK) return rc;
+      const SplitOperand u = split_view(ut, c0 + nb, c0, (int)rest, nb);
+      rc = split_gemm(st, e, u, -1.f, 1.f, W + (c0 + nb), K, 0);
+      if (rc != B200Q_OK) return rc;
     }
   }
   return check_launch("gptq_compensated");

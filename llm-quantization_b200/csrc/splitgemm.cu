@@ -247,6 +247,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       tc_fence_after_sync();
     }
     const bool symm = (flags & SG_SYMM) != 0;
+    const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       const int col0 = n0 + c * 32;
@@ -272,12 +273,28 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       if (symm && col0 > m0 + q * 32 + 31) continue;
       if (row < M) {
         float* dst = C + (int64_t)row * ldc + col0;
+        const bool interior = col0 + 32 <= N && (!symm || col0 + 31 <= row);
+        if (interior && vec_ok) {
+          // the lane's 32 columns are one 128-byte line: 16-byte accesses
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          if (col >= N || (symm && col > row)) continue;
-          const float r = a_eff * __uint_as_float(v[j]);
-          dst[j] = (beta == 0.f) ? r : fmaf(beta, dst[j], r);
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(a_eff * __uint_as_float(v[j]), a_eff * __uint_as_float(v[j + 1]),
+                                   a_eff * __uint_as_float(v[j + 2]), a_eff * __uint_as_float(v[j + 3]));
+            if (beta != 0.f) {
+              const float4 c4 = *reinterpret_cast<const float4*>(dst + j);
+              o.x = fmaf(beta, c4.x, o.x); o.y = fmaf(beta, c4.y, o.y);
+              o.z = fmaf(beta, c4.z, o.z); o.w = fmaf(beta, c4.w, o.w);
+            }
+            *reinterpret_cast<float4*>(dst + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col >= N || (symm && col > row)) continue;
+            const float r = a_eff * __uint_as_float(v[j]);
+            dst[j] = (beta == 0.f) ? r : fmaf(beta, dst[j], r);
+          }
         }
       }
       if (symm) {

@@ -36,6 +36,15 @@ int64_t split_operand_bytes(int rows, int cols);
 int split_operand(cudaStream_t st, const float* src, int64_t ld, int src_rows, int src_cols,
                   bool transpose, int planes, void* buf, SplitOperand* out);
 
+// The [rows, cols] sub-block at (row0, col0) of a prepared operand (col0 a multiple of 8).
+inline SplitOperand split_view(const SplitOperand& full, int64_t row0, int64_t col0, int rows, int cols) {
+  SplitOperand v = full;
+  for (int i = 0; i < 3; ++i) v.p[i] = full.p[i] + row0 * full.ld16 + col0;
+  v.rows = rows;
+  v.cols = cols;
+  return v;
+}
+
 // One-time function attributes of the GEMM kernel (call before recording launches into a graph).
 int split_gemm_prepare();
 
