@@ -153,8 +153,8 @@ static void sgemm(cudaStream_t st, int M, int N, int Kd, float alpha, const floa
 }
 
 // One CTA: Cholesky of the nb x nb (nb <= 64) diagonal block at A (lower, in place; the strict
-// upper part of the block is zeroed) and its inverse into Linv (dense copy, ld = NB) and Linv_big
-// (ld = lda).  info = first non-positive pivot (1-based, offset by j0).
+// upper part of the block is zeroed) and its inverse into the same block of Linv (row stride lda).
+// info = first non-positive pivot (1-based, offset by j0).
 //
 // This kernel sits on the critical path K/64 times, so its LATENCY decides the factorisation time
 // (ncu on the earlier shared-memory versions: one SM, <20 % issue utilisation, ~1000 cycles per
@@ -172,20 +172,40 @@ static void sgemm(cudaStream_t st, int M, int N, int Kd, float alpha, const floa
 // the identity.
 __global__ void __launch_bounds__(256, 1)
 potrf_inv_diag_kernel(float* __restrict__ A, int64_t lda, int nb, float* __restrict__ Linv,
-                      float* __restrict__ Linv_big, int* __restrict__ info, int j0) {
+                      int* __restrict__ info, int j0) {
   constexpr int NB = la::NB;
   static_assert(NB == 64, "register layout assumes 64 x 64 blocks, 16 columns per thread");
   __shared__ __align__(16) float colbuf[2][NB];
   __shared__ __align__(16) float rowbuf[2][NB];
   __shared__ float pivbuf[2];
+  // block <-> registers goes through this tile so that global memory sees whole 256-byte rows per
+  // warp instruction (the per-thread layout alone gave 32 sectors per instruction: ncu showed the
+  // load/store phases at 27 % of the kernel)
+  __shared__ float stage[NB][NB + 1];
   const int tid = threadIdx.x, lane = tid & 31;
   const int r = tid >> 2, q = tid & 3, c0 = q * 16;
+  const bool vec = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15u) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(Linv) & 15u) == 0) && nb == NB;
+  for (int idx = tid; idx < NB * NB / 4; idx += 256) {
+    const int rr = idx >> 4, cc = (idx & 15) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec) {
+      if (cc <= rr) v = *reinterpret_cast<const float4*>(A + (int64_t)rr * lda + cc);
+    } else if (rr < nb) {
+      if (cc < nb) v.x = A[(int64_t)rr * lda + cc];
+      if (cc + 1 < nb) v.y = A[(int64_t)rr * lda + cc + 1];
+      if (cc + 2 < nb) v.z = A[(int64_t)rr * lda + cc + 2];
+      if (cc + 3 < nb) v.w = A[(int64_t)rr * lda + cc + 3];
+    }
+    stage[rr][cc] = v.x; stage[rr][cc + 1] = v.y; stage[rr][cc + 2] = v.z; stage[rr][cc + 3] = v.w;
+  }
+  __syncthreads();
   float a[16], x[16];
   float my_rinv = 1.f;                                   // 1 / L[r][r]
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int c = c0 + i;
-    a[i] = (r < nb && c < nb) ? (c <= r ? A[(int64_t)r * lda + c] : 0.f) : (r == c ? 1.f : 0.f);
+    a[i] = (r < nb && c < nb) ? (c <= r ? stage[r][c] : 0.f) : (r == c ? 1.f : 0.f);
     x[i] = (c == r) ? 1.f : 0.f;
   }
   // (unrolled over the 16 columns of a chunk only: register indices stay static, and the code is a
@@ -253,18 +273,25 @@ potrf_inv_diag_kernel(float* __restrict__ A, int64_t lda, int nb, float* __restr
       }
     }
   }
-  if (r < nb) {
+  // registers -> tile -> global, once for L and once for L^-1
+  auto write_out = [&](const float (&reg)[16], float* __restrict__ dst) {
+    __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int c = c0 + i;
-      if (c >= nb) continue;
-      const float l = (c <= r) ? a[i] : 0.f;
-      const float xi = (c <= r) ? x[i] : 0.f;
-      A[(int64_t)r * lda + c] = l;
-      Linv[r * NB + c] = xi;
-      if (Linv_big != nullptr) Linv_big[(int64_t)r * lda + c] = xi;
+    for (int i = 0; i < 16; ++i) stage[r][c0 + i] = (c0 + i <= r) ? reg[i] : 0.f;
+    __syncthreads();
+    for (int idx = tid; idx < NB * NB / 4; idx += 256) {
+      const int rr = idx >> 4, cc = (idx & 15) * 4;
+      if (vec) {
+        *reinterpret_cast<float4*>(dst + (int64_t)rr * lda + cc) =
+            make_float4(stage[rr][cc], stage[rr][cc + 1], stage[rr][cc + 2], stage[rr][cc + 3]);
+      } else if (rr < nb) {
+        for (int u = 0; u < 4; ++u)
+          if (cc + u < nb) dst[(int64_t)rr * lda + cc + u] = stage[rr][cc + u];
+      }
     }
-  }
+  };
+  write_out(a, A);
+  write_out(x, Linv);
 }
 
 // dst[i][j] = src[K-1-i][K-1-j]   (J * src * J)
@@ -281,7 +308,6 @@ __global__ void reverse_both_kernel(const float* __restrict__ src, float* __rest
 struct LinalgWork {
   float* A;      // [K,K] working copy -> L (lower)
   float* Linv;   // [K,K] -> L^-1 (lower)
-  float* Dinv;   // [NB,NB] inverse of the current diagonal block
   float* T;      // [K,K] scratch for the block products of the triangular inverse
   uint8_t* PA;   // fp16 planes of a GEMM operand (up to the full K x K matrix)
   uint8_t* PB;   // fp16 planes of the second operand (up to half the matrix each way)
@@ -311,7 +337,6 @@ static LinalgWork linalg_layout(void* work, int64_t K) {
   int64_t off = 0;
   w.A = reinterpret_cast<float*>(base + off); off += align(4 * K * K);
   w.Linv = reinterpret_cast<float*>(base + off); off += align(4 * K * K);
-  w.Dinv = reinterpret_cast<float*>(base + off); off += align(4 * la::NB * la::NB);
   w.T = reinterpret_cast<float*>(base + off); off += align(4 * K * K);
   w.PA = base + off; off += align(split_operand_bytes((int)K, (int)K));
   const int half = (int)std::min<int64_t>(K, la::first_half(K) + 128);
@@ -335,8 +360,7 @@ static void leaf_factor_inv(cudaStream_t st, const LinalgWork& w, int64_t ld, in
     float* Ajj = Ab + j * ld + j;
     {
       KernelScope diag_scope("inv_diag", 0, 0, st);
-      potrf_inv_diag_kernel<<<1, 4 * NB, 0, st>>>(Ajj, ld, nb, w.Dinv, Mb + j * ld + j, info,
-                                                  (int)(a0 + j));
+      potrf_inv_diag_kernel<<<1, 4 * NB, 0, st>>>(Ajj, ld, nb, Mb + j * ld + j, info, (int)(a0 + j));
     }
     count_launch();
     const int rem = (int)(n - j - nb);
@@ -344,7 +368,7 @@ static void leaf_factor_inv(cudaStream_t st, const LinalgWork& w, int64_t ld, in
       float* A21 = Ab + (j + nb) * ld + j;
       // L21 = A21 * L11^-T, in place: the panel is one column tile wide (nb <= BN), so each CTA
       // reads exactly the rows it later overwrites
-      sgemm<false, true>(st, rem, nb, nb, 1.f, A21, ld, w.Dinv, NB, 0.f, A21, ld);
+      sgemm<false, true>(st, rem, nb, nb, 1.f, A21, ld, Mb + j * ld + j, ld, 0.f, A21, ld);
       // A22 -= L21 L21^T (lower tiles)
       float* A22 = Ab + (j + nb) * ld + (j + nb);
       sgemm<false, true>(st, rem, rem, nb, -1.f, A21, ld, A21, ld, 1.f, A22, ld, /*tri=*/1);

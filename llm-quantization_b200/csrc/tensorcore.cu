@@ -448,10 +448,14 @@ constexpr int B_BYTES = BN * BK * 2;     // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 constexpr int THREADS = 256;
-constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t TMEM_COLS = 512;     // two 128 x 256 fp32 accumulators
 constexpr int RASTER_M = 16;
 }  // namespace ag
 
+// PERSISTENT: one CTA per SM walks the tile list (stride gridDim.x) with TWO accumulators in TMEM,
+// so the epilogue of tile i (TMEM -> registers, dot with dW from global memory) runs while the MMAs
+// of tile i+1 fill the other accumulator; with the triangular k-ranges the average main loop is only
+// ~34 k-blocks and an exposed epilogue cost 15-20 % of the kernel.
 __global__ void __launch_bounds__(ag::THREADS, 1)
 awq_loss_gemm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_h,
                      const __nv_bfloat16* __restrict__ D, float* __restrict__ tile_loss, int64_t Mtot,
@@ -462,28 +466,31 @@ awq_loss_gemm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_co
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* warp_sum = reinterpret_cast<float*>(tmem_slot + 1);
+  uint64_t* acc_full_bar = empty_bar + STAGES;      // [2] MMA -> epilogue
+  uint64_t* acc_empty_bar = acc_full_bar + 2;       // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (int)((Mtot + BM - 1) / BM);
-  const int band = blockIdx.x / (RASTER_M * tiles_n);
-  const int within = blockIdx.x % (RASTER_M * tiles_n);
-  const int band_rows = min(RASTER_M, tiles_m - band * RASTER_M);
+  const int total_tiles = tiles_m * tiles_n;
   // Hb is LOWER triangular (see h_to_lower_bf16_kernel): output columns [n0, n0 + BN) only receive
   // contributions from k < n0 + BN, so the k-loop of a tile stops there -- half the MMAs of the
-  // dense product overall.  Tiles are issued heaviest (rightmost) first inside every band so the
-  // short ones fill the tail of the wave.
-  const int n_blk = tiles_n - 1 - within / band_rows;
-  const int m_blk = band * RASTER_M + within % band_rows;
-  const int num_kb = (int)((min(K, (int64_t)(n_blk + 1) * BN) + BK - 1) / BK);
+  // dense product overall.  Tile order: bands of RASTER_M tile rows (their dW rows stay in L2),
+  // heaviest (rightmost) tile column first inside a band.
+  auto tile_coords = [&](int t, int& m_blk, int& n_blk, int& num_kb) {
+    const int band = t / (RASTER_M * tiles_n);
+    const int within = t % (RASTER_M * tiles_n);
+    const int band_rows = min(RASTER_M, tiles_m - band * RASTER_M);
+    n_blk = tiles_n - 1 - within / band_rows;
+    m_blk = band * RASTER_M + within % band_rows;
+    num_kb = (int)((min(K, (int64_t)(n_blk + 1) * BN) + BK - 1) / BK);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_d);
     tma_prefetch_desc(&tmap_h);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full_bar[s], 1); mbar_init(&acc_empty_bar[s], 4); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -495,72 +502,95 @@ awq_loss_gemm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_co
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* a_dst = smem + stage * STAGE_BYTES;
-        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-        tma_load_2d(a_dst, &tmap_d, &full_bar[stage], kb * BK, m_blk * BM);
-        tma_load_2d(a_dst + A_BYTES, &tmap_h, &full_bar[stage], kb * BK, n_blk * BN);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m_blk, n_blk, num_kb;
+        tile_coords(t, m_blk, n_blk, num_kb);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = smem + stage * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(a_dst, &tmap_d, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(a_dst + A_BYTES, &tmap_h, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(BM, BN, /*bf16=*/true, /*a_mn=*/false, /*b_mn=*/false);
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int i = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+        int m_blk, n_blk, num_kb;
+        tile_coords(t, m_blk, n_blk, num_kb);
+        const int buf = i & 1;
+        // the epilogue of the tile that used this accumulator two tiles ago must have drained it
+        mbar_wait(&acc_empty_bar[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
         tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_BYTES;
+        const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t da = make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
-          mma_f16_ss(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+            mma_f16_ss(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          mma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        mma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        mma_commit(&acc_full_bar[buf]);
       }
-      mma_commit(tmem_full_bar);
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
-    const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after_sync();
-    float acc = 0.f;
+    int i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      int m_blk, n_blk, num_kb;
+      tile_coords(t, m_blk, n_blk, num_kb);
+      const int buf = i & 1;
+      const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
+      mbar_wait(&acc_full_bar[buf], (uint32_t)((i >> 1) & 1));
+      tc_fence_after_sync();
+      const uint32_t acc_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+      float acc = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      tmem_ld_wait();
-      const int64_t col0 = (int64_t)n_blk * BN + c * 32;
-      if (row < Mtot && col0 < K) {
-        const __nv_bfloat16* dp = D + row * K + col0;
-        if (col0 + 32 <= K) {
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(acc_addr + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        const int64_t col0 = (int64_t)n_blk * BN + c * 32;
+        if (row < Mtot && col0 < K) {
+          const __nv_bfloat16* dp = D + row * K + col0;
+          if (col0 + 32 <= K) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(dp + j);
-            float d[8];
-            unpack16<__nv_bfloat16>(raw, d);
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 raw = *reinterpret_cast<const uint4*>(dp + j);
+              float d[8];
+              unpack16<__nv_bfloat16>(raw, d);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) acc = fmaf(__uint_as_float(v[j + t]), d[t], acc);
+              for (int u = 0; u < 8; ++u) acc = fmaf(__uint_as_float(v[j + u]), d[u], acc);
+            }
+          } else {
+            for (int j = 0; j < 32 && col0 + j < K; ++j)
+              acc = fmaf(__uint_as_float(v[j]), __bfloat162float(dp[j]), acc);
           }
-        } else {
-          for (int j = 0; j < 32 && col0 + j < K; ++j)
-            acc = fmaf(__uint_as_float(v[j]), __bfloat162float(dp[j]), acc);
         }
       }
-    }
+      // the accumulator has been read: hand it back before finishing the reduction
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty_bar[buf]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) warp_sum[q] = acc;
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) tile_loss[((int64_t)m_blk * tiles_n + n_blk) * 4 + q] = acc;
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (threadIdx.x == 0)
-    tile_loss[(int64_t)m_blk * tiles_n + n_blk] = (warp_sum[0] + warp_sum[1]) + (warp_sum[2] + warp_sum[3]);
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
@@ -679,7 +709,7 @@ static AwqWork awq_layout(void* work, int64_t N, int64_t K, int n_cand) {
   int64_t off = 0;
   w.D = reinterpret_cast<__nv_bfloat16*>(base + off); off += align(2 * (int64_t)n_cand * w.rows_pad * K);
   w.Hb = reinterpret_cast<__nv_bfloat16*>(base + off); off += align(2 * K * K);
-  w.tile_loss = reinterpret_cast<float*>(base + off); off += align(4 * (int64_t)n_cand * w.tiles_per_cand);
+  w.tile_loss = reinterpret_cast<float*>(base + off); off += align(16 * (int64_t)n_cand * w.tiles_per_cand);
   w.bytes = off;
   return w;
 }
@@ -832,13 +862,14 @@ int b200q_awq_search_loss(const void* W, int64_t N, int64_t K, int64_t group, in
   {
     KernelScope scope("awq_search_gemm", 0, 2.0 * (double)n_cand * N * K * K, st);
     const int tiles_m = (int)(Mtot / ag::BM);
-    awq_loss_gemm_kernel<<<(unsigned)(tiles_m * w.tiles_n), ag::THREADS, ag::SMEM_BYTES, st>>>(
+    const unsigned ctas = (unsigned)std::min<int64_t>((int64_t)tiles_m * w.tiles_n, kNumSMs);
+    awq_loss_gemm_kernel<<<ctas, ag::THREADS, ag::SMEM_BYTES, st>>>(
         tmap_d, tmap_h, w.D, w.tile_loss, Mtot, K, w.tiles_n);
     count_launch();
     rc = check_launch("awq_loss_gemm");
     if (rc != B200Q_OK) return rc;
   }
-  awq_loss_reduce_kernel<<<n_cand, 256, 0, st>>>(w.tile_loss, w.tiles_per_cand, n_cand, loss);
+  awq_loss_reduce_kernel<<<n_cand, 256, 0, st>>>(w.tile_loss, 4 * w.tiles_per_cand, n_cand, loss);
   count_launch();
   return check_launch("awq_loss_reduce");
 }
