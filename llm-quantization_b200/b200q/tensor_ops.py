@@ -62,16 +62,18 @@ def hessian_finalize(H: torch.Tensor, scale: float, damp: float) -> torch.Tensor
 
 
 def spd_inverse(H: torch.Tensor, ridge: float = 0.0, want_inverse: bool = True,
-                want_upper: bool = False):
+                want_upper: bool = False, owner: int = 0, broadcast: bool = True):
     """inv(H + ridge I) (and/or the upper Cholesky factor U of it, U^T U = inverse) for a CUDA
-    fp32 SPD matrix.  Returns Hinv, U or (Hinv, U).  Under row sharding rank 0 computes and the
-    result is broadcast (the inverse is shared by all row shards)."""
+    fp32 SPD matrix.  Returns Hinv, U or (Hinv, U).  Under row sharding rank `owner` computes and
+    the result is broadcast (the inverse is shared by all row shards); with broadcast=False the
+    other ranks get an uninitialised buffer and the caller broadcasts later, which lets different
+    ranks invert different layers' matrices at the same time."""
     assert H.is_cuda and H.dtype == torch.float32 and H.dim() == 2 and H.shape[0] == H.shape[1]
     K = H.shape[0]
     lib = _lib.load()
     Hinv = torch.empty_like(H) if want_inverse else None
     U = torch.empty_like(H) if want_upper else None
-    if not _dist.is_sharded() or _dist.rank() == 0:
+    if not _dist.is_sharded() or _dist.rank() == owner:
         A = H.contiguous()
         if ridge != 0.0:
             A = hessian_finalize(A.clone(), 1.0, ridge)
@@ -82,26 +84,39 @@ def spd_inverse(H: torch.Tensor, ridge: float = 0.0, want_inverse: bool = True,
                                        None if U is None else U.data_ptr(), K, work.data_ptr(),
                                        info.data_ptr(), _stream())
         _lib.check(rc, "spd_inverse")
-    for t in (Hinv, U):
-        if t is not None:
-            _dist.broadcast(t, 0)
+    if broadcast:
+        for t in (Hinv, U):
+            if t is not None:
+                _dist.broadcast(t, owner)
     if Hinv is not None and U is not None:
         return Hinv, U
     return Hinv if Hinv is not None else U
 
 
-def gptq_compensated(W: torch.Tensor, H: torch.Tensor, n_bit: int, group: int, blocksize: int = 128,
-                     perm: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Error-compensated GPTQ of a CUDA [N,K] weight given its damped Hessian H (fp32 [K,K]).
-    `perm` (act-order) permutes the columns before and restores them after, as GPTQ does."""
-    assert W.is_cuda and W.dim() == 2 and H.shape == (W.shape[1], W.shape[1])
+def compensation_factor(H: torch.Tensor, perm: Optional[torch.Tensor] = None, owner: int = 0,
+                        broadcast: bool = True) -> torch.Tensor:
+    """U = chol(inv(H_perm + 1e-6 I), upper): what the compensated column loop multiplies by."""
+    if perm is not None:
+        H = H[perm][:, perm]
+    return spd_inverse(H.contiguous(), ridge=1e-6, want_inverse=False, want_upper=True, owner=owner,
+                       broadcast=broadcast)
+
+
+def gptq_compensated(W: torch.Tensor, H: Optional[torch.Tensor], n_bit: int, group: int,
+                     blocksize: int = 128, perm: Optional[torch.Tensor] = None,
+                     U: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Error-compensated GPTQ of a CUDA [N,K] weight given its damped Hessian H (fp32 [K,K]) or the
+    factor U = compensation_factor(H, perm) computed earlier.  `perm` (act-order) permutes the
+    columns before and restores them after, as GPTQ does."""
+    assert W.is_cuda and W.dim() == 2
     N, K = W.shape
     Wf = W.float()
     if perm is not None:
         Wf = Wf[:, perm]
-        H = H[perm][:, perm]
     Wf = Wf.contiguous().clone() if Wf.data_ptr() == W.data_ptr() else Wf.contiguous()
-    U = spd_inverse(H.contiguous(), ridge=1e-6, want_inverse=False, want_upper=True)
+    if U is None:
+        assert H is not None and H.shape == (K, K)
+        U = compensation_factor(H, perm)
     Q = torch.empty_like(Wf)
     lib = _lib.load()
     with _on(W.device):

@@ -56,14 +56,31 @@ def gptq_quantize_model_weight(
     group quantizer for the rest (reference: gptq_quantizer.py:58-75)."""
     if verbose:
         print("Applying GPTQ quantization...")
-    def compute(name, _module, W):
-        if name in input_feat:
-            return _gptq_device(W, w_bit, q_group_size, input_feat[name], perp_damp, blocksize,
-                                nsamples, actorder)
-        return _ops.group_fakequant(W, w_bit, q_group_size, symmetric=True)
+    items = [(n, m) for n, m in model.named_modules() if isinstance(m, nn.Linear)]
+    calibrated = [(n, m) for n, m in items if n in input_feat]
+    position = {n: i for i, (n, _) in enumerate(calibrated)}
+    ready = {}
 
-    _pipeline.run_layers([(n, m) for n, m in model.named_modules() if isinstance(m, nn.Linear)],
-                         compute)
+    def compute(name, _module, W):
+        if name not in input_feat:
+            return _ops.group_fakequant(W, w_bit, q_group_size, symmetric=True)
+        if name not in ready:
+            # Under row sharding the inverse of one layer's Hessian is a single-GPU job, so a GROUP
+            # of world-size layers is prepared at once: every rank adds its calibration samples to
+            # each layer's Hessian (all-reduced), then rank j factors layer j of the group while the
+            # others factor theirs, and the factors are broadcast.  Unsharded: groups of one.
+            i = position[name]
+            group = calibrated[i:i + _dist.world_size()]
+            prepared = [_prepare(input_feat[n], m.weight.shape[1], W.device, perp_damp, nsamples,
+                                 actorder, owner=j) for j, (n, m) in enumerate(group)]
+            for j, ((n, _m), p) in enumerate(zip(group, prepared)):
+                if p[2] is not None:
+                    _dist.broadcast(p[2], j)
+                ready[n] = p
+        H, perm, factor = ready.pop(name)
+        return _column_stage(W, w_bit, q_group_size, blocksize, H, perm, factor)
+
+    _pipeline.run_layers(items, compute)
 
 
 # ==================================================================================================
@@ -114,20 +131,38 @@ def _gptq_quantize_layer(
     layer.weight.data = out if out.device == src else out.to(src)
 
 
+def _prepare(input_feat, K: int, device, perp_damp: float, nsamples: int, actorder: bool,
+             owner: int = 0):
+    """(H, perm, factor) of one layer: the damped Hessian, the act-order permutation (compensated
+    mode only) and what the column stage needs from the inverse -- H^-1 in parity mode (built
+    like the reference builds it; its output does not depend on it), U = chol(H^-1) in compensated
+    mode.  Under row sharding `owner` computes the factor; the caller broadcasts it."""
+    from b200q import tensor_ops as _tops
+    if MODE not in ("parity", "compensated"):
+        raise ValueError(f"gptq_quantizer.MODE must be 'parity' or 'compensated', got {MODE!r}")
+    if MODE == "parity" and not BUILD_HESSIAN:
+        return None, None, None
+    H = gptq_hessian(input_feat, K, device, perp_damp, nsamples)
+    if MODE == "compensated":
+        perm = torch.argsort(torch.diag(H), descending=True) if actorder else None
+        return H, perm, _tops.compensation_factor(H, perm, owner=owner, broadcast=False)
+    return H, None, _tops.spd_inverse(H, ridge=1e-6, owner=owner, broadcast=False)
+
+
 def _gptq_device(W: torch.Tensor, n_bit: int, q_group_size: int, input_feat, perp_damp: float,
                  blocksize: int, nsamples: int, actorder: bool) -> torch.Tensor:
     """The per-layer stages on a CUDA-resident [N,K] weight; returns the quantized weight."""
-    K = W.shape[1]
+    H, perm, factor = _prepare(input_feat, W.shape[1], W.device, perp_damp, nsamples, actorder)
+    if factor is not None:
+        _dist.broadcast(factor, 0)
+    return _column_stage(W, n_bit, q_group_size, blocksize, H, perm, factor)
 
-    H = Hinv = None
-    if MODE == "compensated" or BUILD_HESSIAN:
-        H = gptq_hessian(input_feat, K, W.device, perp_damp, nsamples)
-        Hinv = gptq_inverse(H)
 
+def _column_stage(W: torch.Tensor, n_bit: int, q_group_size: int, blocksize: int, H, perm,
+                  factor) -> torch.Tensor:
     if MODE == "compensated":
         from b200q import tensor_ops as _tops
-        perm = torch.argsort(torch.diag(H), descending=True) if actorder else None
-        out = _tops.gptq_compensated(W, H, n_bit, q_group_size, blocksize, perm)
+        out = _tops.gptq_compensated(W, None, n_bit, q_group_size, blocksize, perm, U=factor)
     elif MODE == "parity":
         # The reference's loop rounds column j with s_j = clamp(max_i |W[i,j]| / (2^b-1), 1e-5) and
         # writes q*s back; permuting and un-permuting independent columns is the identity.

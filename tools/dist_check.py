@@ -87,6 +87,34 @@ with torch.no_grad():
         b_sh = awq_quantizer.awq_search_scale_factor(stack(slice(q0, q1)), 4, 128, acts3, n_grid=10)
     b_full = awq_quantizer.awq_search_scale_factor(stack(slice(0, 512)), 4, 128, acts3, n_grid=10)
     results[f"3-layer awq search with look-ahead: sharded {b_sh} == unsharded {b_full}"] = b_sh == b_full
+    # five layers through the grouped GPTQ walker (world-size layers prepared at once, rank j
+    # inverts layer j of the group): parity mode must stay bit-exact, the compensated loop must
+    # agree with the single-GPU run up to the summation order of the all-reduced Hessian
+    Ks5 = [256, 384, 256, 512, 384]
+    W5 = [torch.randn(512, k, generator=gg) * 0.02 for k in Ks5]
+    acts5 = {str(i): [torch.randn(128, k, generator=gg) for _ in range(8)] for i, k in enumerate(Ks5)}
+    def stack5(rows):
+        net = nn.Sequential(*[nn.Linear(k, 1, bias=False) for k in Ks5]).to(dev)
+        for lin, w in zip(net, W5):
+            lin.weight.data = w[rows].clone().to(dev)
+        return net
+    def gather5(t, k):
+        parts = [torch.empty((D.shard_rows(512, world, r)[1] - D.shard_rows(512, world, r)[0], k), device=dev)
+                 for r in range(world)]
+        td.all_gather(parts, t.contiguous())
+        return torch.cat(parts).cpu()
+    for mode in ("parity", "compensated"):
+        gptq_quantizer.MODE = mode
+        sh = stack5(slice(q0, q1))
+        with D.row_sharded():
+            gptq_quantizer.gptq_quantize_model_weight(sh, 4, 128, acts5, actorder=True, verbose=False)
+        full = stack5(slice(0, 512))
+        gptq_quantizer.gptq_quantize_model_weight(full, 4, 128, acts5, actorder=True, verbose=False)
+        agree = min((gather5(a.weight.data, k) == b.weight.data.cpu()).float().mean().item()
+                    for a, b, k in zip(sh, full, Ks5))
+        results[f"grouped gptq walker, {mode}: sharded vs unsharded agreement {agree:.5f}"] = \
+            agree == 1.0 if mode == "parity" else agree >= 0.999
+    gptq_quantizer.MODE = "parity"
 if rank == 0:
     for k, v in results.items():
         print(("PASS " if v else "FAIL ") + k)
