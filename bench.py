@@ -373,6 +373,10 @@ def main():
     launches0 = _lib.launch_count()
     _lib.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    walker_timings = None
+    if os.environ.get("B200Q_WALKER_TIMINGS") and args.method == "gptq":
+        import gptq_quantizer as _gq
+        walker_timings = _gq.TIMINGS = []
     barrier()
     e0.record()
     result = None
@@ -380,6 +384,14 @@ def main():
         result = one_step()
     e1.record()
     barrier()
+    if walker_timings is not None:
+        torch.cuda.synchronize()
+        phases = {}
+        for ph, a, b in walker_timings:
+            phases[ph] = phases.get(ph, 0.0) + a.elapsed_time(b) / args.steps
+        print(f"[rank {rank}] walker phases (ms/step): " +
+              ", ".join(f"{k} {v:.1f}" for k, v in phases.items()), file=sys.stderr, flush=True)
+        _gq.TIMINGS = None
     _lib.profile_enable(False)
     ms_total = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0

@@ -35,6 +35,8 @@ from b200q import pipeline as _pipeline  # noqa: E402
 
 MODE = "parity"
 BUILD_HESSIAN = True
+GROUP_FACTOR = 4    # under row sharding, layers prepared together = GROUP_FACTOR * world size
+TIMINGS = None      # set to a list to collect (phase, ms) CUDA-event pairs from the model walker
 
 
 # ==================================================================================================
@@ -66,21 +68,54 @@ def gptq_quantize_model_weight(
             return _ops.group_fakequant(W, w_bit, q_group_size, symmetric=True)
         if name not in ready:
             # Under row sharding the inverse of one layer's Hessian is a single-GPU job, so a GROUP
-            # of world-size layers is prepared at once: every rank adds its calibration samples to
-            # each layer's Hessian (all-reduced), then rank j factors layer j of the group while the
-            # others factor theirs, and the factors are broadcast.  Unsharded: groups of one.
+            # of layers is prepared at once: every rank adds its calibration samples to each
+            # layer's Hessian (all-reduced), then the ranks factor DIFFERENT layers of the group at
+            # the same time (dealt longest-first by K^3, so a rank that draws an 11008-wide layer
+            # gets fewer 4096-wide ones), and the factors are broadcast.  Unsharded: groups of one.
             i = position[name]
-            group = calibrated[i:i + _dist.world_size()]
-            prepared = [_prepare(input_feat[n], m.weight.shape[1], W.device, perp_damp, nsamples,
-                                 actorder, owner=j) for j, (n, m) in enumerate(group)]
-            for j, ((n, _m), p) in enumerate(zip(group, prepared)):
+            world = _dist.world_size()
+            group = calibrated[i:i + (GROUP_FACTOR * world if world > 1 else 1)]
+            load = [0.0] * world
+            owner = {}
+            for n, m in sorted(group, key=lambda nm: -nm[1].weight.shape[1]):
+                j = min(range(world), key=lambda r: load[r])
+                owner[n] = j
+                load[j] += float(m.weight.shape[1]) ** 3
+            # three phases, so that no collective sits between two ranks' factorisations (an
+            # all-reduce there would make everybody wait for whoever is busy inverting)
+            t0 = _mark()
+            hessians = [_hessian_stage(input_feat[n], m.weight.shape[1], W.device, perp_damp, nsamples)
+                        for n, m in group]
+            t1 = _mark()
+            prepared = [_factor_stage(H, actorder, owner[n]) for (n, _m), H in zip(group, hessians)]
+            t2 = _mark()
+            for (n, _m), p in zip(group, prepared):
                 if p[2] is not None:
-                    _dist.broadcast(p[2], j)
+                    _dist.broadcast(p[2], owner[n])
                 ready[n] = p
+            _lap("hessians", t0, t1)
+            _lap("factors", t1, t2)
+            _lap("broadcast", t2, _mark())
         H, perm, factor = ready.pop(name)
-        return _column_stage(W, w_bit, q_group_size, blocksize, H, perm, factor)
+        t2 = _mark()
+        out = _column_stage(W, w_bit, q_group_size, blocksize, H, perm, factor)
+        _lap("columns", t2, _mark())
+        return out
 
     _pipeline.run_layers(items, compute)
+
+
+def _mark():
+    if TIMINGS is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _lap(phase, e0, e1):
+    if TIMINGS is not None:
+        TIMINGS.append((phase, e0, e1))
 
 
 # ==================================================================================================
@@ -131,18 +166,24 @@ def _gptq_quantize_layer(
     layer.weight.data = out if out.device == src else out.to(src)
 
 
-def _prepare(input_feat, K: int, device, perp_damp: float, nsamples: int, actorder: bool,
-             owner: int = 0):
-    """(H, perm, factor) of one layer: the damped Hessian, the act-order permutation (compensated
-    mode only) and what the column stage needs from the inverse -- H^-1 in parity mode (built
-    like the reference builds it; its output does not depend on it), U = chol(H^-1) in compensated
-    mode.  Under row sharding `owner` computes the factor; the caller broadcasts it."""
-    from b200q import tensor_ops as _tops
+def _hessian_stage(input_feat, K: int, device, perp_damp: float, nsamples: int):
+    """The damped Hessian of one layer (all-reduced under row sharding), or None when parity mode
+    is told to skip the work the reference's output does not depend on."""
     if MODE not in ("parity", "compensated"):
         raise ValueError(f"gptq_quantizer.MODE must be 'parity' or 'compensated', got {MODE!r}")
     if MODE == "parity" and not BUILD_HESSIAN:
+        return None
+    return gptq_hessian(input_feat, K, device, perp_damp, nsamples)
+
+
+def _factor_stage(H, actorder: bool, owner: int = 0):
+    """(H, perm, factor): the act-order permutation (compensated mode only) and what the column
+    stage needs from the inverse -- H^-1 in parity mode (built like the reference builds it; its
+    output does not depend on it), U = chol(H^-1) in compensated mode.  Under row sharding only
+    rank `owner` computes the factor and the caller broadcasts it; no collective happens here."""
+    from b200q import tensor_ops as _tops
+    if H is None:
         return None, None, None
-    H = gptq_hessian(input_feat, K, device, perp_damp, nsamples)
     if MODE == "compensated":
         perm = torch.argsort(torch.diag(H), descending=True) if actorder else None
         return H, perm, _tops.compensation_factor(H, perm, owner=owner, broadcast=False)
@@ -152,7 +193,8 @@ def _prepare(input_feat, K: int, device, perp_damp: float, nsamples: int, actord
 def _gptq_device(W: torch.Tensor, n_bit: int, q_group_size: int, input_feat, perp_damp: float,
                  blocksize: int, nsamples: int, actorder: bool) -> torch.Tensor:
     """The per-layer stages on a CUDA-resident [N,K] weight; returns the quantized weight."""
-    H, perm, factor = _prepare(input_feat, W.shape[1], W.device, perp_damp, nsamples, actorder)
+    H = _hessian_stage(input_feat, W.shape[1], W.device, perp_damp, nsamples)
+    H, perm, factor = _factor_stage(H, actorder)
     if factor is not None:
         _dist.broadcast(factor, 0)
     return _column_stage(W, n_bit, q_group_size, blocksize, H, perm, factor)
