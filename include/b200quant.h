@@ -64,6 +64,16 @@ int b200q_profile_query(const char* name, double* total_ms, int64_t* launches, d
  * pairs.  *mismatches must come back 0.  Synchronises the stream. */
 int b200q_selftest_div(int64_t n_quotients, uint64_t seed, int64_t* mismatches, void* stream);
 
+/* ---- packed integer export (the reference stores no codes) -----
+ * Each row of the uint8 code plane [N,K] (values < 2^n_bit, n_bit in [1,8]) becomes a
+ * little-endian bit stream: code k occupies bits [k*n_bit, (k+1)*n_bit), stored as
+ * b200q_packed_words_per_row(K, n_bit) = ceil(K*n_bit/32) uint32 words, zero padded. */
+int64_t b200q_packed_words_per_row(int64_t K, int n_bit);
+int b200q_pack_codes(const uint8_t* codes, int64_t N, int64_t K, int n_bit, uint32_t* packed,
+                     void* stream);
+int b200q_unpack_codes(const uint32_t* packed, int64_t N, int64_t K, int n_bit, uint8_t* codes,
+                       void* stream);
+
 /* ---- torch-CPU log2 semantics, exported for the CPU test-suite -------------------
  * rne(log2f(r)) and floor(log2f(m)) as torch's CPU kernel evaluates them are step
  * functions of r; the library tabulates the step positions on the host at load

@@ -33,7 +33,10 @@ SEARCH_STUB = False
 def _feat_matrix(feats, device) -> torch.Tensor:
     """The per-batch statistics of one layer as an [n, K] matrix on `device`.  The reference takes
     a list of [K] tensors; an [n, K] tensor iterates (and sums) row by row and is accepted as is."""
-    if isinstance(feats, torch.Tensor):
+    from b200q.streaming import ActivationStream
+    if isinstance(feats, ActivationStream):
+        stacked = feats.stats_matrix(device)
+    elif isinstance(feats, torch.Tensor):
         stacked = feats.reshape(feats.shape[0], -1)
     else:
         stacked = torch.stack([f.reshape(-1) for f in feats])
@@ -133,7 +136,8 @@ def awq_search_scale_factor(
         feats = input_feat[name]
         # 2-D [tokens, K] features are raw activations: their per-batch mean|x| is the statistic
         # the quantizer ranks channels by (quantization_utils.py:231); 1-D features already are it
-        if isinstance(feats, torch.Tensor) and feats.dim() == 2:
+        from b200q.streaming import ActivationStream
+        if isinstance(feats, ActivationStream) or (isinstance(feats, torch.Tensor) and feats.dim() == 2):
             stat_rows = feats
         else:
             stat_rows = _stat_rows(feats, W.device)

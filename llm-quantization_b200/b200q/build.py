@@ -30,6 +30,7 @@ SOURCES = {
     "tensorcore.cu": [],
     "linalg.cu": [],
     "splitgemm.cu": [],
+    "packing.cu": [],
 }
 
 

@@ -144,6 +144,11 @@ def gram_matrix_begin(input_feat: Sequence, in_features: int, device) -> Pending
     layer's kernels behind this one and pick the result up later with gram_matrix_end."""
     device = torch.device(device)
     K = in_features
+    from .streaming import ActivationStream
+    if isinstance(input_feat, ActivationStream):
+        assert not input_feat.normalize and input_feat.in_features == K
+        H = input_feat.matrix_sum(device)            # (already all-reduced: nothing left in flight)
+        return PendingGram(H, None, max(1, input_feat.total_rows(device)))
     if isinstance(input_feat, torch.Tensor):
         X = input_feat.reshape(-1, K)
     else:
@@ -217,6 +222,13 @@ def gptq_hessian(input_feat: Sequence, in_features: int, device, perp_damp: floa
     require_cuda()
     device = torch.device(device)
     K = in_features
+    from .streaming import ActivationStream
+    if isinstance(input_feat, ActivationStream):
+        # batches were folded in as they were captured (streaming.py); `[:nsamples]` was applied by
+        # the stream's max_batches, the divisor is every batch seen, as in the reference
+        assert input_feat.normalize and input_feat.in_features == K
+        return hessian_finalize(input_feat.matrix_sum(device), 1.0 / max(1, input_feat.batches_seen),
+                                perp_damp)
     if isinstance(input_feat, torch.Tensor):
         feats_total = input_feat.shape[0]
         runs = [(input_feat[:nsamples].reshape(-1, K), 1)] if input_feat.dim() == 2 else \

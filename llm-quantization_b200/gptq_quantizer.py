@@ -228,11 +228,16 @@ def gptq_calibrate_hessian(
     calib_samples: List[torch.Tensor],
     nsamples: int = 128,
     verbose: bool = True,
+    streaming: bool = False,
 ) -> Dict[str, List[torch.Tensor]]:
     """Capture, per Linear, the [tokens, in_features] input of every calibration batch, kept on the
     device it was produced on (reference: gptq_quantizer.py:210-264).  These lists are the 2-D
-    `input_feat` layout `_gptq_quantize_layer` turns into H with the tensor-core kernel."""
+    `input_feat` layout `_gptq_quantize_layer` turns into H with the tensor-core kernel.
+    streaming=True (not in the reference) folds every batch into a running Hessian inside the hook
+    instead (b200q.streaming.ActivationStream), so no activations are kept; the returned dict can be
+    passed to gptq_quantize_model_weight like the lists."""
     import tqdm
+    from b200q.streaming import ActivationStream
 
     captured: Dict[str, List[torch.Tensor]] = {}
 
@@ -241,7 +246,13 @@ def gptq_calibrate_hessian(
             x = inputs[0] if isinstance(inputs, tuple) else inputs
             if x.dim() > 2:
                 x = x.reshape(-1, x.shape[-1])
-            captured.setdefault(name, []).append(x.detach())
+            if streaming:
+                if name not in captured:
+                    captured[name] = ActivationStream(x.shape[-1], normalize=True,
+                                                      max_batches=nsamples, keep_stats=False)
+                captured[name].add(x)
+            else:
+                captured.setdefault(name, []).append(x.detach())
         return hook
 
     device = torch.device("cuda" if torch.cuda.is_available() else "cpu")

@@ -355,3 +355,39 @@ def gptq_compensated(W: torch.Tensor, H: torch.Tensor, n_bit: int, group: int,
             Err[:, j - c0] = e
         Wd[:, c1:] -= Err @ U[c0:c1, c1:]
     return Q.to(W.dtype)
+
+
+# --------------------------------------------------------------------------------------------------
+# packed integer export.  The reference stores no codes, so there is
+# nothing to pin against: this is the specification of the layout (PARITY UNPINNED by construction).
+# --------------------------------------------------------------------------------------------------
+def pack_codes(codes, n_bit: int):
+    """uint8 codes [N, K] -> uint32 words [N, ceil(K*n_bit/32)]: each row is a little-endian bit
+    stream with code k at bits [k*n_bit, (k+1)*n_bit)."""
+    import numpy as np
+    c = np.asarray(codes, dtype=np.uint64) & ((1 << n_bit) - 1)
+    N, K = c.shape
+    words = (K * n_bit + 31) // 32
+    out = np.zeros((N, words), dtype=np.uint64)
+    for k in range(K):
+        bit = k * n_bit
+        w, off = bit // 32, bit % 32
+        out[:, w] |= (c[:, k] << off) & 0xFFFFFFFF
+        if off + n_bit > 32:
+            out[:, w + 1] |= c[:, k] >> (32 - off)
+    return out.astype(np.uint32)
+
+
+def unpack_codes(words, K: int, n_bit: int):
+    import numpy as np
+    w = np.asarray(words, dtype=np.uint64)
+    N = w.shape[0]
+    out = np.zeros((N, K), dtype=np.uint8)
+    for k in range(K):
+        bit = k * n_bit
+        i, off = bit // 32, bit % 32
+        v = w[:, i] >> off
+        if off + n_bit > 32:
+            v = v | (w[:, i + 1] << (32 - off))
+        out[:, k] = (v & ((1 << n_bit) - 1)).astype(np.uint8)
+    return out

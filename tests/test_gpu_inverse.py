@@ -22,7 +22,7 @@ def rel(got, want):
     return ((got.double() - want.double()).abs().max() / want.double().abs().max()).item()
 
 
-@pytest.mark.parametrize("K", [64, 128, 200, 256, 384, 1000, 2048])
+@pytest.mark.parametrize("K", [64, 128, 200, 256, 384, 1000, 1001, 1544, 2048])
 def test_inverse_and_upper_factor_vs_fp64(K):
     from b200q import tensor_ops as T
     H = spd(K, K)
@@ -64,3 +64,27 @@ def test_non_spd_is_reported():
     rc = lib.b200q_spd_inverse(H.data_ptr(), out.data_ptr(), None, K, work.data_ptr(), info.data_ptr(),
                                torch.cuda.current_stream().cuda_stream)
     assert rc == 0 and int(info.item()) == 6
+
+
+def test_replayed_graph_sees_new_data():
+    """The factorisation of a given size is recorded into a CUDA graph on first use and replayed:
+    a second, different matrix of the same size must give ITS inverse, and a non-positive pivot
+    deep inside the recursion (past the 512-column leaves) must still be reported."""
+    from b200q import tensor_ops as T
+    K = 1200
+    for seed in (1, 2, 3):
+        H = spd(K, seed)
+        Hinv = T.spd_inverse(H.cuda())
+        assert rel(Hinv.cpu(), torch.linalg.inv(H.double())) < 1e-4, seed
+    import ctypes
+    from b200q import _lib
+    lib = _lib.load()
+    H = torch.eye(K, device="cuda")
+    H[900, 900] = -2.0
+    work = torch.empty(lib.b200q_spd_inverse_workspace(K), dtype=torch.uint8, device="cuda")
+    out = torch.empty_like(H)
+    for _ in range(2):                                   # capture, then replay
+        info = torch.zeros(1, dtype=torch.int32, device="cuda")
+        rc = lib.b200q_spd_inverse(H.data_ptr(), out.data_ptr(), None, K, work.data_ptr(), info.data_ptr(),
+                                   torch.cuda.current_stream().cuda_stream)
+        assert rc == 0 and int(info.item()) == 901

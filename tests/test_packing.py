@@ -1,0 +1,62 @@
+"""Packed export layout: the oracle's bit-stream packer (CPU) and the CUDA kernels against it."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import quant_oracle as O
+
+
+def test_oracle_layout_known_vectors():
+    # 4 bits: eight codes per word, lowest nibble first
+    assert O.pack_codes(np.array([[1, 2, 3, 4, 5, 6, 7, 8]], dtype=np.uint8), 4)[0, 0] == 0x87654321
+    # 3 bits: code 10 straddles words 0 and 1 (bits 30..32)
+    c = np.zeros((1, 32), dtype=np.uint8)
+    c[0, 10] = 0b101
+    w = O.pack_codes(c, 3)
+    assert w.shape == (1, 3) and w[0, 0] == (0b01 << 30) and w[0, 1] == 0b1 and w[0, 2] == 0
+    rng = np.random.default_rng(0)
+    for b in range(1, 9):
+        for K in (1, 37, 100, 128):
+            codes = rng.integers(0, 1 << b, size=(5, K), dtype=np.uint8)
+            assert np.array_equal(O.unpack_codes(O.pack_codes(codes, b), K, b), codes)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("N,K", [(3, 37), (64, 128), (5, 100), (17, 4096)])
+def test_kernels_match_oracle(b, N, K):
+    from b200q import export as E
+    rng = np.random.default_rng(b * 1000 + K)
+    codes = rng.integers(0, 1 << b, size=(N, K), dtype=np.uint8)
+    d = torch.from_numpy(codes).cuda()
+    packed = E.pack_codes(d, b)
+    want = O.pack_codes(codes, b)
+    assert np.array_equal(packed.cpu().numpy().view(np.uint32), want)
+    assert torch.equal(E.unpack_codes(packed, K, b), d)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("b,G", [(4, 128), (3, 128), (8, 64), (4, -1)])
+def test_uniform_export_round_trips_to_the_fake_quantized_weight(dtype, b, G):
+    from b200q import export as E, ops
+    g = torch.Generator().manual_seed(b + 7)
+    W = (torch.randn(96, 512, generator=g) * 0.05).to(dtype).cuda()
+    rec = E.export_uniform(W, b, G)
+    assert rec["qweight"].shape == (96, 512 * b // 32) and rec["qweight"].dtype == torch.int32
+    assert torch.equal(E.dequantize(rec), ops.group_fakequant(W, b, G))
+    # the codes are the oracle's integers
+    want = O.uniform_group_quant(W.cpu(), b, G)
+    codes = E.unpack_codes(rec["qweight"], 512, b).cpu()
+    assert torch.equal(codes.to(torch.int32), want["codes"].reshape(96, 512))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_gptq_export_round_trips(dtype):
+    from b200q import export as E, ops
+    g = torch.Generator().manual_seed(11)
+    W = (torch.randn(200, 384, generator=g) * 0.05).to(dtype).cuda()
+    rec = E.export_gptq_parity(W, 4)
+    assert rec["bits"] == 5
+    assert torch.equal(E.dequantize(rec), ops.gptq_parity_quant(W, 4))
