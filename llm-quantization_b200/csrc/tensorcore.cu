@@ -42,8 +42,21 @@ sample_stats_partial_kernel(const T* __restrict__ X, int64_t rows_per_sample, in
   const int64_t nvec = n / VEC;
   double acc = 0.0;
   float amax = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // four 16-byte loads in flight per thread (HBM-bound pass: T*K*sz bytes read once)
+  for (; i + 3 * stride < nvec; i += 4 * stride) {
+    float v[4][VEC];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load_vec<T>(p + (i + u * stride) * VEC, v[u]);
+    float sq = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { sq = fmaf(v[u][j], v[u][j], sq); amax = fmaxf(amax, fabsf(v[u][j])); }
+    acc += (double)sq;
+  }
+  for (; i < nvec; i += stride) {
     float v[VEC];
     load_vec<T>(p + i * VEC, v);
     float sq = 0.f;
@@ -161,19 +174,28 @@ constexpr uint32_t TMEM_COLS = 256;
 constexpr int RASTER_M = 16;     // tile rows per rasterisation band
 }  // namespace hg
 
-template <bool BF16>
+// PER_SAMPLE (GPTQ Hessian of 16-bit activations, no staging pass): TMA reads the caller's tensor,
+// the MMAs accumulate ONE calibration sample at a time, and the epilogue warps fold each finished
+// sample into a running total kept in TMEM columns [256, 512) as  total += chunk / (||x|| + 1e-5)^2
+// on the FP32 pipe -- the per-sample normalisation of gptq_quantizer.py:143 applied to the exact
+// Gram matrix of the sample instead of to every activation, and round-to-nearest accumulation
+// across samples (the tensor core's own accumulate truncates).
+template <bool BF16, bool PER_SAMPLE>
 __global__ void __launch_bounds__(hg::THREADS, 1)
 hessian_gemm_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ partial,
-                    int64_t K, int64_t T, int64_t tokens_per_split, int tiles_n) {
+                    int64_t K, int64_t T, int64_t tokens_per_split, int tiles_n,
+                    const float* __restrict__ norms, int kb_per_sample) {
   using namespace hg;
+  constexpr uint32_t kTmemCols = PER_SAMPLE ? 512u : TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;        // MMA -> epilogue: (chunk) accumulator complete
+  uint64_t* chunk_free_bar = tmem_full_bar + 1;        // epilogue -> MMA: chunk accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(chunk_free_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -196,6 +218,10 @@ hessian_gemm_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
   const int64_t t0 = (int64_t)z * tokens_per_split;
   const int64_t t1 = min(T, t0 + tokens_per_split);
   const int num_kb = (int)((t1 - t0 + BKT - 1) / BKT);
+  // chunks of the k loop that are accumulated inside the tensor core: the whole loop, or one sample
+  const int chunk_kb = PER_SAMPLE ? kb_per_sample : max(num_kb, 1);
+  const int num_chunks = (num_kb + chunk_kb - 1) / chunk_kb;
+  const int sample0 = PER_SAMPLE ? (int)(t0 / ((int64_t)kb_per_sample * BKT)) : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap);
@@ -204,9 +230,10 @@ hessian_gemm_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(chunk_free_bar, 4);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -240,39 +267,97 @@ hessian_gemm_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
       constexpr uint32_t idesc = make_idesc_f16(BM, BN, BF16, /*a_mn=*/true, /*b_mn=*/true);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_BYTES;
-#pragma unroll
-        for (int k = 0; k < BKT / UMMA_K; ++k) {
-          // 16 tokens = 16 rows of 128 bytes further down every box
-          const uint32_t koff = k * UMMA_K * 128;
-          const uint64_t da = make_smem_desc_sw128(a_addr + koff, BOX_BYTES, 1024);
-          const uint64_t db = make_smem_desc_sw128(b_addr + koff, BOX_BYTES, 1024);
-          mma_f16_ss(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+      int kb = 0;
+      for (int ch = 0; ch < num_chunks; ++ch) {
+        if (PER_SAMPLE && ch > 0) {                  // the previous sample has been folded in
+          mbar_wait(chunk_free_bar, (uint32_t)((ch - 1) & 1));
+          tc_fence_after_sync();
         }
-        mma_commit(&empty_bar[stage]);          // frees the smem stage once these MMAs retire
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        const int kb_end = min(num_kb, kb + chunk_kb);
+        for (bool first = true; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BKT / UMMA_K; ++k) {
+            // 16 tokens = 16 rows of 128 bytes further down every box
+            const uint32_t koff = k * UMMA_K * 128;
+            const uint64_t da = make_smem_desc_sw128(a_addr + koff, BOX_BYTES, 1024);
+            const uint64_t db = make_smem_desc_sw128(b_addr + koff, BOX_BYTES, 1024);
+            mma_f16_ss(tmem_base, da, db, idesc, (first && k == 0) ? 0u : 1u);
+          }
+          first = false;
+          mma_commit(&empty_bar[stage]);          // frees the smem stage once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(tmem_full_bar);                // (chunk) accumulator complete
       }
-      mma_commit(tmem_full_bar);                // accumulator complete
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> global (fp32) =====
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
     float* dst_base = partial + (int64_t)z * K * K;
     const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
-    if (num_kb > 0) {
-      mbar_wait(tmem_full_bar, 0);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    auto sample_weight = [&](int ch) {
+      const float a = 1.f / (norms[sample0 + ch] + 1e-5f);     // gptq_quantizer.py:143
+      return a * a;
+    };
+    if (PER_SAMPLE) {
+      for (int ch = 0; ch + 1 < num_chunks; ++ch) {
+        mbar_wait(tmem_full_bar, (uint32_t)(ch & 1));
+        tc_fence_after_sync();
+        const float wgt = sample_weight(ch);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32], t[32];
+          tmem_ld_32x32(lane_base + (uint32_t)(c * 32), v);
+          if (ch > 0) {
+            tmem_ld_32x32(lane_base + (uint32_t)(BN + c * 32), t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = __float_as_uint(fmaf(wgt, __uint_as_float(v[j]), __uint_as_float(t[j])));
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(wgt * __uint_as_float(v[j]));
+          }
+          tmem_st_32x32(lane_base + (uint32_t)(BN + c * 32), v);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(chunk_free_bar);
+      }
+    }
+    if (num_chunks > 0) {
+      mbar_wait(tmem_full_bar, (uint32_t)((num_chunks - 1) & 1));
       tc_fence_after_sync();
     }
+    const float last_wgt = (PER_SAMPLE && num_chunks > 0) ? sample_weight(num_chunks - 1) : 1.f;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
-      if (num_kb > 0) {
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
+      if (num_chunks > 0) {
+        tmem_ld_32x32(lane_base + (uint32_t)(c * 32), v);
+        if (PER_SAMPLE) {
+          if (num_chunks > 1) {
+            uint32_t t[32];
+            tmem_ld_32x32(lane_base + (uint32_t)(BN + c * 32), t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = __float_as_uint(fmaf(last_wgt, __uint_as_float(v[j]), __uint_as_float(t[j])));
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(last_wgt * __uint_as_float(v[j]));
+          }
+        } else {
+          tmem_ld_wait();
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0u;
@@ -303,7 +388,7 @@ hessian_gemm_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
 // =================================================================================================
@@ -412,7 +497,8 @@ struct HessianWork {
 static HessianWork hessian_layout(void* work, int64_t T, int64_t K, int n_samples,
                                   int straight /* 0, 1, or -1 = size for either */) {
   HessianWork w;
-  w.chunks = (int)std::max<int64_t>(1, std::min<int64_t>(64, (2 * kNumSMs) / std::max(1, n_samples)));
+  // CTAs of the sample-statistics pass: chunks x n_samples, ~8 per SM to keep HBM busy
+  w.chunks = (int)std::max<int64_t>(1, std::min<int64_t>(64, (8 * kNumSMs + n_samples - 1) / std::max(1, n_samples)));
   w.splits = straight < 0 ? std::max(hessian_splits(K, T, false), hessian_splits(K, T, true))
                           : hessian_splits(K, T, straight != 0);
   auto align = [](int64_t x) { return (x + 255) / 256 * 256; };
@@ -737,14 +823,22 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
   B200Q_REQUIRE(T < (1ll << 31) && K < (1ll << 31), "hessian_accum: dimension too large");
   const double flops = 2.0 * (double)T * (double)K * (double)K;
 
-  // A plain Gram matrix (no per-sample normalisation, no norms wanted) of 16-bit activations needs
-  // no staging pass at all: fp16 / bf16 products are exact in the fp32 accumulator, so TMA reads the
-  // caller's tensor directly.  Everything else goes through stats + prescale into fp16.
-  const bool direct = !normalize && norms_out == nullptr && (dtype == B200Q_F16 || dtype == B200Q_BF16);
-  const bool bf16_ops = direct && dtype == B200Q_BF16;
+  // 16-bit activations need no staging pass: fp16 / bf16 products are exact in the fp32
+  // accumulator, so TMA reads the caller's tensor directly.
+  //   direct      : plain Gram matrix (no normalisation, no norms wanted) -- no other pass at all
+  //   per_sample  : GPTQ normalisation with samples of >= 512 rows in whole 64-token blocks -- one
+  //                 read-only pass for the sample norms, then the kernel folds each sample in with
+  //                 its weight (PER_SAMPLE above)
+  // Everything else (fp32 input, short or ragged samples) goes through stats + prescale into fp16.
+  const bool sixteen = dtype == B200Q_F16 || dtype == B200Q_BF16;
+  const bool direct = sixteen && !normalize && norms_out == nullptr;
+  const bool per_sample = sixteen && normalize && rows_per_sample % hg::BKT == 0 &&
+                          rows_per_sample >= 8 * hg::BKT;
+  const bool in_place = direct || per_sample;
+  const bool bf16_ops = in_place && dtype == B200Q_BF16;
   HessianWork w = hessian_layout(work, T, K, n_samples, (direct && !accumulate) ? 1 : 0);
   if (!direct) {
-    KernelScope scope("hessian_prescale", 3.0 * T * K * elem_size(dtype), 0, st);
+    KernelScope scope("hessian_prescale", (per_sample ? 1.0 : 3.0) * T * K * elem_size(dtype), 0, st);
     B200Q_DISPATCH_DTYPE(dtype, Tt, {
       constexpr int VEC = ST<Tt>::VEC;
       B200Q_REQUIRE((rows_per_sample * K) % VEC == 0, "hessian_accum: sample not 16-byte sized");
@@ -753,12 +847,15 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
                                                           rows_per_sample, K, w.partial_st);
       sample_stats_finish_kernel<<<1, 256, 0, st>>>(w.partial_st, w.chunks, n_samples, w.stats,
                                                     normalize);
-      const int64_t total_vec = T * K / VEC;
-      const int blocks = (int)std::min<int64_t>((total_vec + 255) / 256, (int64_t)kNumSMs * 16);
-      prescale_kernel<Tt><<<blocks, 256, 0, st>>>(static_cast<const Tt*>(X), w.Xs, rows_per_sample,
-                                                  K, total_vec, w.stats);
+      count_launch(2);
+      if (!per_sample) {
+        const int64_t total_vec = T * K / VEC;
+        const int blocks = (int)std::min<int64_t>((total_vec + 255) / 256, (int64_t)kNumSMs * 16);
+        prescale_kernel<Tt><<<blocks, 256, 0, st>>>(static_cast<const Tt*>(X), w.Xs, rows_per_sample,
+                                                    K, total_vec, w.stats);
+        count_launch();
+      }
     });
-    count_launch(3);
     int rc = check_launch("hessian_accum/prescale");
     if (rc != B200Q_OK) return rc;
   }
@@ -767,42 +864,60 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
                     cudaMemcpyDeviceToDevice, st);
 
   CUtensorMap tmap;
-  int rc = make_tmap_2d_16bit(&tmap, direct ? X : static_cast<const void*>(w.Xs), T, K, hg::BKT,
+  int rc = make_tmap_2d_16bit(&tmap, in_place ? X : static_cast<const void*>(w.Xs), T, K, hg::BKT,
                               hg::BOX_CH, bf16_ops);
   if (rc != B200Q_OK) return rc;
-  // (per-device attribute: the call is cheap and idempotent)
-  if (cudaFuncSetAttribute(hessian_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  // (per-device attribute: the calls are cheap and idempotent)
+  if (cudaFuncSetAttribute(hessian_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            hg::SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(hessian_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaFuncSetAttribute(hessian_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           hg::SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(hessian_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           hg::SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(hessian_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            hg::SMEM_BYTES) != cudaSuccess)
     return fail(B200Q_ECUDA, "hessian_gemm: cannot raise shared memory");
   const int64_t kblocks = (T + hg::BKT - 1) / hg::BKT;
-  const int64_t kb_per_split = (kblocks + w.splits - 1) / w.splits;
-  const int64_t tokens_per_split = kb_per_split * hg::BKT;
+  int splits = w.splits;
+  int64_t tokens_per_split;
+  const int kb_per_sample = (int)(rows_per_sample / hg::BKT);
+  if (per_sample) {
+    // splits cover whole samples
+    const int64_t samples_per_split = ((int64_t)n_samples + splits - 1) / splits;
+    splits = (int)(((int64_t)n_samples + samples_per_split - 1) / samples_per_split);
+    tokens_per_split = samples_per_split * rows_per_sample;
+  } else {
+    const int64_t kb_per_split = (kblocks + splits - 1) / splits;
+    tokens_per_split = kb_per_split * hg::BKT;
+  }
   // one split, nothing to add to and no scale to undo: the tiles go straight into H
-  const bool straight = direct && w.splits == 1 && !accumulate;
+  const bool straight = in_place && splits == 1 && !accumulate;
   float* gemm_out = straight ? H : w.partial;
   {
     KernelScope scope("hessian_gemm", 0, flops, st);
     const int tiles_n = (int)((K + hg::BN - 1) / hg::BN);
     const int tiles_m = (int)((K + hg::BM - 1) / hg::BM);
-    dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)w.splits);
-    if (bf16_ops)
-      hessian_gemm_kernel<true><<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(tmap, gemm_out, K, T,
-                                                                           tokens_per_split, tiles_n);
-    else
-      hessian_gemm_kernel<false><<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(tmap, gemm_out, K, T,
-                                                                            tokens_per_split, tiles_n);
+    dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)splits);
+    const float* norms = w.stats + n_samples;
+#define B200Q_HG_LAUNCH(BF, PS)                                                                   \
+    hessian_gemm_kernel<BF, PS><<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(                        \
+        tmap, gemm_out, K, T, tokens_per_split, tiles_n, norms, kb_per_sample)
+    if (per_sample) {
+      if (bf16_ops) B200Q_HG_LAUNCH(true, true); else B200Q_HG_LAUNCH(false, true);
+    } else {
+      if (bf16_ops) B200Q_HG_LAUNCH(true, false); else B200Q_HG_LAUNCH(false, false);
+    }
+#undef B200Q_HG_LAUNCH
     count_launch();
     rc = check_launch("hessian_gemm");
     if (rc != B200Q_OK) return rc;
   }
   if (!straight) {
-    KernelScope scope("hessian_reduce", sizeof(float) * (double)(w.splits + 1) * K * K, 0, st);
+    KernelScope scope("hessian_reduce", sizeof(float) * (double)(splits + 1) * K * K, 0, st);
     const int64_t KK = K * K;
     const int blocks = (int)std::min<int64_t>((KK / 4 + 255) / 256, (int64_t)kNumSMs * 16);
-    hessian_reduce_kernel<<<blocks, 256, 0, st>>>(w.partial, w.splits, KK,
-                                                  direct ? nullptr : w.stats + 2 * n_samples, H,
+    hessian_reduce_kernel<<<blocks, 256, 0, st>>>(w.partial, splits, KK,
+                                                  in_place ? nullptr : w.stats + 2 * n_samples, H,
                                                   accumulate);
     count_launch();
     rc = check_launch("hessian_reduce");

@@ -106,3 +106,26 @@ def test_gram_of_16bit_activations_reads_them_directly(dtype, n, rows, K):
     assert torch.equal(H, H.T)
     H2 = T.hessian_accum(X, rows, H.clone(), normalize=False)
     assert rel_err(H2.cpu(), 2 * want) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n,rows,K", [(4, 512, 512), (3, 2048, 384), (9, 1024, 1000), (1, 512, 256)])
+def test_per_sample_path_for_16bit_activations(dtype, n, rows, K):
+    """Normalised Hessian of 16-bit samples of >= 512 rows: no fp16 staging copy -- the kernel
+    accumulates one sample at a time and folds it in with weight 1/(||x||+1e-5)^2.  Products are
+    exact, so only fp32 summation error is left."""
+    from b200q import tensor_ops as T
+    from b200q import _lib
+    feats = make_feats(31 + K + n, n, rows, K, dtype)
+    X = torch.cat(feats).cuda()
+    H, norms = T.hessian_accum(X, rows, return_norms=True)
+    want = torch.zeros(K, K, dtype=torch.float64)
+    for f in feats:
+        fn = f.double() / (f.double().norm() + 1e-5)
+        want += fn.T @ fn
+    assert rel_err(H.cpu(), want) < 2e-5
+    assert torch.equal(H, H.T)
+    torch.testing.assert_close(norms.cpu(), torch.stack([f.double().norm() for f in feats]).float(),
+                               rtol=2e-6, atol=0)
+    H2 = T.hessian_accum(X, rows, H.clone())
+    assert rel_err(H2.cpu(), 2 * want) < 2e-5
