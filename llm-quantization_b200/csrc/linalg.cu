@@ -8,7 +8,7 @@
 // factored, and the off-diagonal block of M as two more products.  Those products -- nearly all of
 // the K^3 work -- and the final M^T M run on the tcgen05 tensor cores with fp32 operands split
 // into fp16 planes and round-to-nearest accumulation across k-chunks (splitgemm.cu).  Blocks of
-// <= 512 columns are factored on the FP32 pipe: a one-CTA register-resident kernel per 64 x 64
+// <= 1024 columns are factored on the FP32 pipe: a one-CTA register-resident kernel per 64 x 64
 // diagonal block, SIMT GEMMs (8x8 register tiles, 128x128x16 CTA tiles) for the rest.
 //
 // For the error-compensated GPTQ loop the quantity needed is U = chol(H^-1, upper).  With J the
@@ -316,7 +316,15 @@ struct LinalgWork {
 };
 
 namespace la {
-constexpr int LEAF = 512;   // blocks up to this size are factored by the SIMT path
+// blocks up to this size are factored by the SIMT path (B200Q_INVERSE_LEAF overrides, read once)
+inline int64_t leaf() {
+  static const int64_t v = []() {
+    const char* e = std::getenv("B200Q_INVERSE_LEAF");
+    const long x = e != nullptr ? std::atol(e) : 0;
+    return (int64_t)((x >= 64 && x <= 4096) ? x : 1024);   // measured: 128..1024 within 10 %, 1024 best
+  }();
+  return v;
+}
 inline int64_t first_half(int64_t n) { return ((n / 2 + 127) / 128) * 128; }
 // fp16 planes per operand of the tensor-core products.  Two (22 bits) are enough: measured against
 // an fp64 inverse the result is as accurate as with three (33 bits) -- the error that remains is
@@ -406,10 +414,10 @@ static void leaf_factor_inv(cudaStream_t st, const LinalgWork& w, int64_t ld, in
 //                                  L22, M22                  (recursion)
 //                                  M21 = -M22 (L21 M11)      (two GEMMs, triangular k ranges)
 // so that nearly all of the K^3 work sits in a few large products, which run on the tensor cores
-// (splitgemm.cu); only blocks of <= LEAF columns use the FP32 pipe.
+// (splitgemm.cu); only blocks of <= la::leaf() columns use the FP32 pipe.
 static int factor_inv(cudaStream_t st, const LinalgWork& w, int64_t K, int64_t a0, int64_t n,
                       int* info) {
-  if (n <= la::LEAF) {
+  if (n <= la::leaf()) {
     leaf_factor_inv(st, w, K, a0, n, info);
     return B200Q_OK;
   }

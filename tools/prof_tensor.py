@@ -1,16 +1,28 @@
-"""One launch of each tensor-core kernel at a Llama-2-7B layer shape (target of ncu --set full)."""
+"""One or two launches of every tensor-core kernel at the Llama-2-7B shapes of the headline bench
+(262144 calibration tokens; K = 4096 and 11008) -- the target of the `ncu --set full` capture that
+also provides bench.py's roofline.traffic (profiles/traffic_r1.json)."""
 import sys
 from pathlib import Path
 REPO = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(REPO / "llm-quantization_b200"))
 import torch
 from b200q import tensor_ops as T
-K, N, tokens = 4096, 4096, 65536
-X = torch.randn(tokens, K, device="cuda", dtype=torch.bfloat16)
-W = torch.randn(N, K, device="cuda") * 0.02
-mask = torch.zeros(K, dtype=torch.uint8, device="cuda"); mask[::100] = 1
-for _ in range(2):
-    H = T.hessian_finalize(T.hessian_accum(X, 2048, normalize=False), 1.0 / tokens, 0.0)
-    T.awq_search_losses(W, H, mask, 4, 128, torch.linspace(1, 2, 20).tolist())
-torch.cuda.synchronize()
+tokens = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
+cands = torch.linspace(1, 2, 20).tolist()
+for K in (4096, 11008):
+    X = torch.randn(tokens, K, device="cuda", dtype=torch.bfloat16)
+    W = torch.randn(4096, K, device="cuda") * 0.02
+    mask = torch.zeros(K, dtype=torch.uint8, device="cuda"); mask[::100] = 1
+    H = T.hessian_accum(X, 2048, normalize=False)            # Gram matrix, activations read in place
+    T.awq_search_losses(W, H, mask, 4, 128, cands)           # delta + fold + persistent loss GEMM
+    if K == 4096:
+        Hn = T.hessian_accum(X, 2048)                        # GPTQ Hessian, per-sample accumulation
+        T.hessian_finalize(Hn, 1.0 / (tokens // 2048), 0.01)
+        T.spd_inverse(Hn)                                    # recursive factor-and-invert (split GEMMs)
+        Hn[range(K), range(K)] += 0.01
+        T.gptq_compensated(W.clone(), Hn, 4, 128)            # block kernel + lazy update on tcgen05
+    torch.cuda.synchronize()
+    del X, W, H
+    T.release_workspace()
+    torch.cuda.empty_cache()
 print("ok")
