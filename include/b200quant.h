@@ -191,7 +191,9 @@ int b200q_apot_quant(const void* w, void* out, uint8_t* level_idx, float* best_s
  * sample lists are fed as several calls).  norms_out (optional, fp32 [n_samples]) receives
  * ||X_i||_F.  work: b200q_hessian_workspace(T, K, n_samples) bytes of device scratch.
  * K must be a multiple of 8.  normalize = 0 drops the per-sample factor (plain X^T X, the
- * Gram matrix the AWQ search measures its reconstruction error with). */
+ * Gram matrix the AWQ search measures its reconstruction error with).  fp16 / bf16 activations
+ * are read in place by TMA (no staging copy) for normalize = 0, and for normalize = 1 when
+ * rows_per_sample is a multiple of 64 and >= 512; fp32 input is staged as scaled fp16. */
 int64_t b200q_hessian_workspace(int64_t T, int64_t K, int n_samples);
 int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, int64_t K, int dtype,
                         int normalize, float* H, int accumulate, float* norms_out, void* work,

@@ -16,6 +16,10 @@
 //                     TMA producer, warp 1 = MMA issuer (one thread), warps 4-7 = epilogue
 //                     (tcgen05.ld -> fp32 stores).
 //   4. reduce         H (+)= 2^-2s * sum_z P[z], splits added in a fixed order (deterministic).
+// 16-bit activations skip the staging: the plain Gram matrix (AWQ search) runs stage 3 directly on
+// the caller's tensor, and the normalised Hessian of samples of >= 512 rows runs stage 1 and a
+// PER_SAMPLE variant of stage 3 that folds each sample in with its weight a_i^2 (see the kernel).
+// Only tiles touching the upper triangle run (SYRK); a single split is written straight into H.
 #include <algorithm>
 #include <cmath>
 #include <mutex>
