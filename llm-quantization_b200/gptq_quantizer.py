@@ -228,14 +228,27 @@ def gptq_calibrate_hessian(
     calib_samples: List[torch.Tensor],
     nsamples: int = 128,
     verbose: bool = True,
-    streaming: bool = False,
 ) -> Dict[str, List[torch.Tensor]]:
     """Capture, per Linear, the [tokens, in_features] input of every calibration batch, kept on the
     device it was produced on (reference: gptq_quantizer.py:210-264).  These lists are the 2-D
-    `input_feat` layout `_gptq_quantize_layer` turns into H with the tensor-core kernel.
-    streaming=True (not in the reference) folds every batch into a running Hessian inside the hook
-    instead (b200q.streaming.ActivationStream), so no activations are kept; the returned dict can be
-    passed to gptq_quantize_model_weight like the lists."""
+    `input_feat` layout `_gptq_quantize_layer` turns into H with the tensor-core kernel."""
+    return _calibrate(model, calib_samples, nsamples, verbose, streaming=False)
+
+
+@torch.no_grad()
+def gptq_calibrate_hessian_streaming(
+    model: nn.Module,
+    calib_samples: List[torch.Tensor],
+    nsamples: int = 128,
+    verbose: bool = True,
+):
+    """Not in the reference: like gptq_calibrate_hessian, but every batch is
+    folded into a running Hessian inside the hook (b200q.streaming.ActivationStream), so no
+    activations are kept.  The returned dict goes to gptq_quantize_model_weight like the lists."""
+    return _calibrate(model, calib_samples, nsamples, verbose, streaming=True)
+
+
+def _calibrate(model, calib_samples, nsamples, verbose, streaming):
     import tqdm
     from b200q.streaming import ActivationStream
 

@@ -42,7 +42,7 @@ def test_calibration_hook_streams_and_the_walker_accepts_streams():
     net = nn.Sequential(nn.Linear(256, 384, bias=False), nn.Linear(384, 256, bias=False)).cuda()
     samples = [torch.randn(4, 32, 256) for _ in range(5)]
     lists = gq.gptq_calibrate_hessian(net, samples, nsamples=128, verbose=False)
-    streams = gq.gptq_calibrate_hessian(net, samples, nsamples=128, verbose=False, streaming=True)
+    streams = gq.gptq_calibrate_hessian_streaming(net, samples, nsamples=128, verbose=False)
     assert set(lists) == set(streams) == {"0", "1"}
     assert streams["0"].batches_seen == 5 and streams["0"].stat_rows == []
     from b200q import tensor_ops as T
