@@ -81,3 +81,23 @@ def test_quadratic_form_is_folded_onto_the_lower_triangle():
     sym = ((H.double() + H.double().T) / 2).float()
     want = O.awq_search_losses(W, sym, hot, 4, 128, cands)
     assert ((got - want).abs() / want.abs()).max().item() < 1e-2
+
+
+def test_many_tiles_per_cta():
+    """1280 output tiles on 148 persistent CTAs: every CTA walks ~9 tiles, so both TMEM accumulators
+    are reused several times (the small cases above give each CTA a single tile)."""
+    from b200q import tensor_ops as T
+    N, K, n_cand = 2048, 1024, 20
+    W, feats, hot = setup(N, K, 5, n=4, rows=256)
+    X = torch.cat(feats)
+    H = T.gram_matrix(feats, K, "cuda")
+    mask = torch.zeros(K, dtype=torch.uint8)
+    mask[hot] = 1
+    cands = torch.linspace(1.0, 2.0, n_cand, dtype=torch.float64).tolist()
+    got = T.awq_search_losses(W.cuda(), H, mask.cuda(), 4, 128, cands).cpu().double()
+    want = O.awq_search_losses(W, ((X.double().T @ X.double()) / X.shape[0]).float(), hot, 4, 128, cands)
+    assert ((got - want).abs() / want).max().item() < 1e-2
+    assert int(torch.argmin(got)) == int(torch.argmin(want))
+    # deterministic: the same launch gives the same bits
+    again = T.awq_search_losses(W.cuda(), H, mask.cuda(), 4, 128, cands).cpu().double()
+    assert torch.equal(got, again)
