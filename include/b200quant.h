@@ -165,6 +165,17 @@ int b200q_smoothquant_layer(const void* W, void* out, int64_t N, int64_t K, int6
                             int n_bit, const float* act_scale, float alpha, int act_dtype,
                             float* s, float* work, int dtype, void* stream);
 
+/* ---- SmoothQuant alpha sweep (ref: smooth_quant_quantizer.py:327-371, a stub in the reference) --
+ * err[a] (+)= sum_{i,k} ((Q(W[i,k] / S[a,k]) * S[a,k] - W[i,k]) * act_weight[k])^2 for a < n_alpha,
+ * Q = the asymmetric group quantizer of b200q_group_fakequant.  S is [n_alpha, K] fp32 (one
+ * smoothing-scale vector per candidate alpha, from b200q_smooth_scale), err is fp64 [n_alpha] on
+ * the device (accumulate != 0 adds to it, so a model walk needs no host synchronisation).
+ * W is read from HBM once for all alphas; no N x K temporary is written. */
+int64_t b200q_smooth_alpha_workspace(int64_t N, int64_t K, int64_t group, int n_alpha);
+int b200q_smooth_alpha_errors(const void* W, int64_t N, int64_t K, int64_t group, int n_bit,
+                              const float* S, int n_alpha, const float* act_weight, int dtype,
+                              void* work, double* err, int accumulate, void* stream);
+
 /* ---- POT ------------------------------------------------------------------------------
  * ref: pot_apot_quantizer.py:25-115.  w is [n_groups, group] contiguous; grid_host is the
  * HOST array torch.arange(0.01, 2.01, 0.01) materialised by the caller (n_grid floats).

@@ -43,6 +43,9 @@ SIGNATURES = {
     "b200q_profile_enable": (None, [C.c_int]),
     "b200q_profile_query": (C.c_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(c_i64),
                                       C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "b200q_smooth_alpha_workspace": (c_i64, [c_i64, c_i64, c_i64, C.c_int]),
+    "b200q_smooth_alpha_errors": (C.c_int, [c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp, C.c_int, c_vp,
+                                            C.c_int, c_vp, c_vp, C.c_int, c_vp]),
     "b200q_packed_words_per_row": (c_i64, [c_i64, C.c_int]),
     "b200q_pack_codes": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp]),
     "b200q_unpack_codes": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp]),

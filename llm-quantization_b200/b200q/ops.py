@@ -357,3 +357,29 @@ def smoothquant_layer(W: torch.Tensor, act_scale: torch.Tensor, alpha: float, n_
                                                  work.data_ptr(), dtype_code(W), _stream())
     _lib.check(rc, "smoothquant_layer")
     return out, s
+
+
+def smooth_alpha_errors(W: torch.Tensor, S: torch.Tensor, act_weight: torch.Tensor, n_bit: int,
+                        group: int, err: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp64 [n_alpha] on the device: for every row S[a] of smoothing scales, the squared error of
+    the smoothed-then-quantized weight mapped back and weighted by act_weight (see the header).
+    Adds to `err` when given, so a model walk never synchronises."""
+    assert W.is_cuda and W.dim() == 2 and S.dim() == 2 and S.shape[1] == W.shape[1]
+    W = W.contiguous()
+    N, K = W.shape
+    S = _f32(S, W.device)
+    a = _f32(act_weight, W.device)
+    n_alpha = S.shape[0]
+    accumulate = err is not None
+    if err is None:
+        err = torch.empty(n_alpha, dtype=torch.float64, device=W.device)
+    lib = _lib.load()
+    nbytes = lib.b200q_smooth_alpha_workspace(N, K, group, n_alpha)
+    assert nbytes > 0, "in_features not divisible by the group size"
+    work = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
+    with _on(W.device):
+        rc = lib.b200q_smooth_alpha_errors(W.data_ptr(), N, K, group, n_bit, S.data_ptr(), n_alpha,
+                                           a.data_ptr(), dtype_code(W), work.data_ptr(),
+                                           err.data_ptr(), int(accumulate), _stream())
+    _lib.check(rc, "smooth_alpha_errors")
+    return err

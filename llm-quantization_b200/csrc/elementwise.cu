@@ -552,6 +552,80 @@ int launch_awq_delta(const void* W, void* D, const uint8_t* salient, int64_t N, 
   return check_launch("awq_delta");
 }
 
+// =================================================================================================
+// SmoothQuant alpha sweep (ref: smooth_quant_quantizer.py:327-371, a stub there): for every candidate
+// alpha a, with s_a the smoothing scale of that alpha,
+//     err[a] (+)= sum_{i,k} ( (Q(W[i,k] / s_a[k]) * s_a[k] - W[i,k]) * act[k] )^2
+// i.e. the error of the smoothed-then-quantized weight mapped back to the original basis and
+// weighted by the calibration activation magnitude.  One warp owns one quantization group and
+// sweeps ALL alphas over it (min/max pass + quantize pass per alpha), so W comes from HBM once and
+// from L1 afterwards; nothing of size N x K is written.  Per-warp partial sums, reduced in a fixed
+// order by smooth_alpha_reduce_kernel (deterministic).
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+smooth_alpha_err_kernel(const T* __restrict__ W, const float* __restrict__ S,
+                        const float* __restrict__ act, int64_t n_groups, int64_t G, int64_t K,
+                        float maxint, int n_alpha, double* __restrict__ partial) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  __shared__ double accs[8][32];                       // per warp, per alpha (n_alpha <= 32)
+  if (lane < n_alpha) accs[wib][lane] = 0.0;
+  __syncwarp();
+  for (int64_t g = warp; g < n_groups; g += nwarps) {
+    const int64_t off = g * G;
+    for (int a = 0; a < n_alpha; ++a) {                // the group stays in L1 across the alphas
+      const float* sa = S + (int64_t)a * K;
+      float mx = -INFINITY, mn = INFINITY;
+      for (int64_t i = lane; i < G; i += 32) {
+        const float x = ST<T>::rnd(__fdiv_rn(to_f(W[off + i]), sa[(off + i) % K]));
+        mx = fmaxf(mx, x); mn = fminf(mn, x);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      }
+      float scale, zp;
+      group_params<T, false>(mx, mn, maxint, scale, zp);
+      float e2 = 0.f;
+      for (int64_t i = lane; i < G; i += 32) {
+        const int64_t k = (off + i) % K;
+        const float w = to_f(W[off + i]);
+        const float sv = sa[k];
+        const float x = ST<T>::rnd(__fdiv_rn(w, sv));
+        const float code = clampf(ST<T>::rnd(rint_then_clamped(ST<T>::rnd(__fdiv_rn(x, scale))) + zp),
+                                  0.f, maxint);
+        const float deq = ST<T>::rnd(ST<T>::rnd(code - zp) * scale);
+        const float e = (ST<T>::rnd(deq * sv) - w) * act[k];
+        e2 = fmaf(e, e, e2);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+      if (lane == 0) accs[wib][a] += (double)e2;
+    }
+  }
+  __syncwarp();
+  if (lane < n_alpha) partial[(int64_t)lane * nwarps + warp] = accs[wib][lane];
+}
+
+__global__ void smooth_alpha_reduce_kernel(const double* __restrict__ partial, int64_t nwarps,
+                                           int n_alpha, double* __restrict__ err, int accumulate) {
+  const int a = blockIdx.x;
+  if (a >= n_alpha) return;
+  __shared__ double sm[256];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < nwarps; i += blockDim.x) s += partial[(int64_t)a * nwarps + i];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) err[a] = (accumulate ? err[a] : 0.0) + sm[0];
+}
+
 // any group length: one warp per group, two passes (the second re-reads through L2).
 template <typename T, bool SYM, int COLOP>
 __global__ void __launch_bounds__(256)
@@ -1185,6 +1259,43 @@ int b200q_selftest_div(int64_t n_quotients, uint64_t seed, int64_t* mismatches, 
     set_error(buf);
   }
   return B200Q_OK;
+}
+
+static int64_t smooth_alpha_warps(int64_t n_groups) {
+  return std::min<int64_t>(n_groups, (int64_t)kNumSMs * 8 * 8);
+}
+
+int64_t b200q_smooth_alpha_workspace(int64_t N, int64_t K, int64_t group, int n_alpha) {
+  if (N <= 0 || K <= 0 || n_alpha <= 0) return 0;
+  const int64_t G = group > 0 ? group : K;
+  if (K % G != 0) return 0;
+  const int64_t warps = (smooth_alpha_warps(N * (K / G)) + 7) / 8 * 8;
+  return (int64_t)sizeof(double) * warps * n_alpha + 256;
+}
+
+int b200q_smooth_alpha_errors(const void* W, int64_t N, int64_t K, int64_t group, int n_bit,
+                              const float* S, int n_alpha, const float* act_weight, int dtype,
+                              void* work, double* err, int accumulate, void* stream) {
+  B200Q_REQUIRE(W && S && act_weight && work && err, "smooth_alpha_errors: null pointer");
+  B200Q_REQUIRE(N > 0 && K > 0 && n_alpha > 0 && n_alpha <= 32, "smooth_alpha_errors: bad shape (1..32 alphas)");
+  B200Q_REQUIRE(n_bit >= 1 && n_bit <= 16, "smooth_alpha_errors: n_bit must be in [1,16]");
+  const int64_t G = group > 0 ? group : K;
+  B200Q_REQUIRE(K % G == 0, "smooth_alpha_errors: in_features not divisible by group size");
+  B200Q_REQUIRE((reinterpret_cast<uintptr_t>(work) & 7u) == 0, "smooth_alpha_errors: unaligned workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n_groups = N * (K / G);
+  const int blocks = (int)((smooth_alpha_warps(n_groups) + 7) / 8);
+  const int64_t nwarps = (int64_t)blocks * 8;
+  double* partial = static_cast<double*>(work);
+  KernelScope scope("smooth_alpha_errors", (double)N * K * elem_size(dtype), 0, st);
+  const float maxint = (float)((1 << n_bit) - 1);
+  B200Q_DISPATCH_DTYPE(dtype, T,
+                       (smooth_alpha_err_kernel<T><<<blocks, 256, 0, st>>>(
+                           static_cast<const T*>(W), S, act_weight, n_groups, G, K, maxint, n_alpha,
+                           partial)));
+  smooth_alpha_reduce_kernel<<<n_alpha, 256, 0, st>>>(partial, nwarps, n_alpha, err, accumulate);
+  count_launch(2);
+  return check_launch("smooth_alpha_errors");
 }
 
 }  // extern "C"

@@ -210,19 +210,21 @@ def smoothquant_search_alpha(model: nn.Module, calib_samples: List[torch.Tensor]
         best = (lo + hi) / 2.0
     else:
         alphas = torch.linspace(float(lo), float(hi), int(n_grid), dtype=torch.float64).tolist()
-        totals = torch.zeros(len(alphas), dtype=torch.float64)
+        totals = None
         for name, m in model.named_modules():
             if not isinstance(m, nn.Linear) or name not in act_scales:
                 continue
             W = _ops.to_device(m.weight.data)
             a = act_scales[name].to(W.device, torch.float32).clamp(min=1e-5)
-            for i, alpha in enumerate(alphas):
-                s, s_dtype = _layer_smoothing_scale(W, act_scales[name], alpha)
-                q = _ops.group_fakequant(W.to(s_dtype), w_bit, q_group_size, colop=_ops.COLOP_DIV,
-                                         colvec=s)
-                err = (_ops.col_scale(q, s, mul=True).float() - W.float()) * a
-                totals[i] += float((err.double() ** 2).sum().item())
-        best = alphas[int(torch.argmin(totals).item())] if totals.sum() > 0 else (lo + hi) / 2.0
+            # one smoothing-scale vector per alpha ([n_grid, K], tiny), then ONE kernel sweeps all
+            # alphas over the weight: W is read once, the errors accumulate on the device
+            scales = [_layer_smoothing_scale(W, act_scales[name], alpha) for alpha in alphas]
+            S = torch.stack([s for s, _ in scales])
+            totals = _ops.smooth_alpha_errors(W.to(scales[0][1]), S, a, w_bit, q_group_size, totals)
+        if totals is not None:
+            totals = _dist.allreduce_sum(totals)
+        best = alphas[int(torch.argmin(totals).item())] if totals is not None and \
+            float(totals.sum().item()) > 0 else (lo + hi) / 2.0
     if verbose:
         print(f"  -> Using alpha: {best:.2f}")
     return float(best)

@@ -391,3 +391,21 @@ def unpack_codes(words, K: int, n_bit: int):
             v = v | (w[:, i + 1] << (32 - off))
         out[:, k] = (v & ((1 << n_bit) - 1)).astype(np.uint8)
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# a18  smoothquant_search_alpha's measure      ref: smooth_quant_quantizer.py:327-371 (a stub there)
+# PARITY UNPINNED: the reference returns the midpoint; this restates the measure the drop-in uses.
+# --------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def smooth_alpha_errors(W: torch.Tensor, S: torch.Tensor, act_weight: torch.Tensor, n_bit: int,
+                        group: int) -> torch.Tensor:
+    """fp64 [n_alpha]: sum ((Q(W / S[a]) * S[a] - W) * act_weight)^2 with Q = uniform_group_quant."""
+    out = []
+    for s in S:
+        smoothed = W / s.to(W.dtype)
+        q = uniform_group_quant(smoothed, n_bit, group)["out"]
+        back = q * s.to(W.dtype)
+        err = (back.double() - W.double()) * act_weight.double()
+        out.append((err ** 2).sum())
+    return torch.stack(out)
