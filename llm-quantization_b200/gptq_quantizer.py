@@ -75,12 +75,7 @@ def gptq_quantize_model_weight(
             i = position[name]
             world = _dist.world_size()
             group = calibrated[i:i + (GROUP_FACTOR * world if world > 1 else 1)]
-            load = [0.0] * world
-            owner = {}
-            for n, m in sorted(group, key=lambda nm: -nm[1].weight.shape[1]):
-                j = min(range(world), key=lambda r: load[r])
-                owner[n] = j
-                load[j] += float(m.weight.shape[1]) ** 3
+            owner = _deal_layers([(n, m.weight.shape[1]) for n, m in group], world)
             # three phases, so that no collective sits between two ranks' factorisations (an
             # all-reduce there would make everybody wait for whoever is busy inverting)
             t0 = _mark()
@@ -103,6 +98,19 @@ def gptq_quantize_model_weight(
         return out
 
     _pipeline.run_layers(items, compute)
+
+
+def _deal_layers(layers, world: int) -> Dict[str, int]:
+    """{name: rank} for a group of (name, in_features) pairs: longest factorisation first (cost
+    ~ in_features^3), each to the rank with the least work so far.  Deterministic, so every rank
+    derives the same assignment without talking."""
+    load = [0.0] * max(1, world)
+    owner: Dict[str, int] = {}
+    for name, k in sorted(layers, key=lambda nk: (-nk[1], nk[0])):
+        j = min(range(len(load)), key=lambda r: (load[r], r))
+        owner[name] = j
+        load[j] += float(k) ** 3
+    return owner
 
 
 def _mark():

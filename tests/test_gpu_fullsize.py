@@ -67,3 +67,47 @@ def test_pot_apot_properties_full_matrix(N, K):
     assert torch.equal(scale[:, None] * lv.cuda()[lidx.long()], out)
     # row-shard consistency for POT (APOT's grid depends on the global element count)
     assert torch.equal(pot_quantize_tensor(w[100:164].contiguous(), 4, 128), q[100:164])
+
+
+@pytest.mark.parametrize("K", [4096, 11008])
+def test_inverse_defining_identities_at_llama_sizes(K):
+    """BASELINE sizes (Llama-2-7B in_features): several levels of the recursive factorisation, the
+    tensor-core products with chunked accumulation, the CUDA-graph replay.  Size-independent
+    properties: H^-1 H = I, symmetry, U upper triangular with U^T U = H^-1."""
+    from b200q import tensor_ops as T
+    g = torch.Generator(device="cuda").manual_seed(K)
+    X = torch.randn(K + 512, K, device="cuda", generator=g)
+    H = (X.T @ X) / X.shape[0]
+    H += 0.01 * torch.diag(H).mean() * torch.eye(K, device="cuda")
+    del X
+    for _ in range(2):                                   # capture, then replay
+        Hinv, U = T.spd_inverse(H, want_inverse=True, want_upper=True)
+    eye = torch.eye(K, device="cuda")
+    assert (Hinv @ H - eye).abs().max().item() < 2e-3    # fp32 check product; fp64 residual is ~1e-5
+    assert torch.equal(Hinv, Hinv.T)
+    assert torch.count_nonzero(U.tril(-1)).item() == 0
+    rel = ((U.T @ U) - Hinv).abs().max() / Hinv.abs().max()
+    assert rel.item() < 1e-4
+
+
+def test_hessian_and_gram_at_llama_token_counts():
+    """128 samples x 2048 tokens of bf16 activations (the bench's calibration set) at K = 4096:
+    linearity in the sample set and agreement of the two tensor-core paths where they must agree."""
+    from b200q import tensor_ops as T
+    K, n, rows = 4096, 128, 2048
+    g = torch.Generator(device="cuda").manual_seed(7)
+    X = torch.randn(n * rows, K, device="cuda", generator=g, dtype=torch.bfloat16)
+    G_all = T.hessian_accum(X, rows, normalize=False)
+    half = n // 2 * rows
+    G_two = T.hessian_accum(X[half:], rows, T.hessian_accum(X[:half], rows, normalize=False),
+                            normalize=False)
+    assert ((G_all - G_two).abs().max() / G_all.abs().max()).item() < 1e-5
+    assert torch.equal(G_all, G_all.T)
+    # normalised Hessian: every sample has trace 1 (up to the 1e-5 in the denominator)
+    H, norms = T.hessian_accum(X, rows, return_norms=True)
+    assert abs(torch.diag(H).sum().item() - n) < 1e-2 * n
+    # a sample's block of the Gram matrix, scaled by its norm, is its term of H
+    H0 = T.hessian_accum(X[:rows], rows)
+    G0 = T.hessian_accum(X[:rows], rows, normalize=False)
+    want = G0 / (norms[0] + 1e-5) ** 2
+    assert ((H0 - want).abs().max() / want.abs().max()).item() < 1e-5

@@ -137,3 +137,21 @@ def test_product_modules_do_not_import_the_oracle():
     for path in list(pkg.glob("*.py")) + list((pkg / "b200q").glob("*.py")):
         text = path.read_text()
         assert "import oracle" not in text and "from oracle" not in text, path
+
+
+def test_gptq_group_dealing_balances_the_inverse_work():
+    """Row-sharded GPTQ deals the layers of a group to the ranks by K^3, longest first: with the
+    Llama-2-7B mix (six 4096-wide and one 11008-wide Linear per block) no rank may end up with
+    more than ~one 11008-wide layer over the mean."""
+    import gptq_quantizer as gq
+    block = [("q", 4096), ("k", 4096), ("v", 4096), ("o", 4096), ("gate", 4096), ("up", 4096),
+             ("down", 11008)]
+    layers = [(f"{i}.{n}", k) for i in range(5) for n, k in block][:32]
+    owner = gq._deal_layers(layers, 8)
+    assert set(owner) == {n for n, _ in layers} and set(owner.values()) <= set(range(8))
+    load = [0.0] * 8
+    for n, k in layers:
+        load[owner[n]] += float(k) ** 3
+    assert max(load) <= sum(load) / 8 + 11008.0 ** 3
+    assert owner == gq._deal_layers(list(reversed(layers)), 8), "assignment must not depend on order"
+    assert gq._deal_layers(layers, 1) == {n: 0 for n, _ in layers}
