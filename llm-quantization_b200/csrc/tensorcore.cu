@@ -178,12 +178,15 @@ constexpr uint32_t TMEM_COLS = 256;
 constexpr int RASTER_M = 16;     // tile rows per rasterisation band
 }  // namespace hg
 
-// PER_SAMPLE (GPTQ Hessian of 16-bit activations, no staging pass): TMA reads the caller's tensor,
-// the MMAs accumulate ONE calibration sample at a time, and the epilogue warps fold each finished
-// sample into a running total kept in TMEM columns [256, 512) as  total += chunk / (||x|| + 1e-5)^2
-// on the FP32 pipe -- the per-sample normalisation of gptq_quantizer.py:143 applied to the exact
-// Gram matrix of the sample instead of to every activation, and round-to-nearest accumulation
-// across samples (the tensor core's own accumulate truncates).
+// PER_SAMPLE = chunked accumulation.  The tensor core aligns every product to the accumulator's
+// exponent and TRUNCATES it, so a sum of N same-sign terms (the diagonal of X^T X) comes out low by
+// about N * 2^-24 relative: 0.2 % after 37 000 tokens (measured).  The MMAs therefore accumulate
+// only `kb_per_sample` 64-token blocks at a time and the epilogue warps fold each finished chunk
+// into a running total kept in TMEM columns [256, 512) on the FP32 pipe (round to nearest).
+// With `norms` given (GPTQ Hessian of 16-bit activations, no staging pass) a chunk is exactly one
+// calibration sample and is folded in as  total += chunk / (||x|| + 1e-5)^2 -- the per-sample
+// normalisation of gptq_quantizer.py:143 applied to the sample's exact Gram matrix instead of to
+// every activation.
 template <bool BF16, bool PER_SAMPLE>
 __global__ void __launch_bounds__(hg::THREADS, 1)
 hessian_gemm_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ partial,
@@ -305,6 +308,7 @@ hessian_gemm_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
     const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     auto sample_weight = [&](int ch) {
+      if (norms == nullptr) return 1.f;                         // plain chunked accumulation
       const float a = 1.f / (norms[sample0 + ch] + 1e-5f);     // gptq_quantizer.py:143
       return a * a;
     };
@@ -884,7 +888,8 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
   const int64_t kblocks = (T + hg::BKT - 1) / hg::BKT;
   int splits = w.splits;
   int64_t tokens_per_split;
-  const int kb_per_sample = (int)(rows_per_sample / hg::BKT);
+  // chunk of the k loop accumulated inside the tensor core: one sample, or 2048 tokens
+  const int kb_per_sample = per_sample ? (int)(rows_per_sample / hg::BKT) : 32;
   if (per_sample) {
     // splits cover whole samples
     const int64_t samples_per_split = ((int64_t)n_samples + splits - 1) / splits;
@@ -902,11 +907,12 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
     const int tiles_n = (int)((K + hg::BN - 1) / hg::BN);
     const int tiles_m = (int)((K + hg::BM - 1) / hg::BM);
     dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)splits);
-    const float* norms = w.stats + n_samples;
+    const float* norms = per_sample ? w.stats + n_samples : nullptr;
 #define B200Q_HG_LAUNCH(BF, PS)                                                                   \
     hessian_gemm_kernel<BF, PS><<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(                        \
         tmap, gemm_out, K, T, tokens_per_split, tiles_n, norms, kb_per_sample)
-    if (per_sample) {
+    const bool chunked = per_sample || kblocks / splits > kb_per_sample;   // long k loops only
+    if (chunked) {
       if (bf16_ops) B200Q_HG_LAUNCH(true, true); else B200Q_HG_LAUNCH(false, true);
     } else {
       if (bf16_ops) B200Q_HG_LAUNCH(true, false); else B200Q_HG_LAUNCH(false, false);
