@@ -22,6 +22,7 @@
 // Only tiles touching the upper triangle run (SYRK); a single split is written straight into H.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -888,8 +889,11 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
   const int64_t kblocks = (T + hg::BKT - 1) / hg::BKT;
   int splits = w.splits;
   int64_t tokens_per_split;
-  // chunk of the k loop accumulated inside the tensor core: one sample, or 2048 tokens
-  const int kb_per_sample = per_sample ? (int)(rows_per_sample / hg::BKT) : 32;
+  // chunk of the k loop accumulated inside the tensor core: one sample; 2048 tokens for the staged
+  // Hessian; 4096 tokens for the plain Gram matrix (diagonal low by <= 2.4e-4, an eighth of the
+  // bf16 rounding its consumer, the AWQ search, applies -- measured on one box: 2048-token chunks
+  // cost 5.5 % of this kernel, no chunking leaves the diagonal 0.2 % low)
+  const int kb_per_sample = per_sample ? (int)(rows_per_sample / hg::BKT) : (direct ? 64 : 32);
   if (per_sample) {
     // splits cover whole samples
     const int64_t samples_per_split = ((int64_t)n_samples + splits - 1) / splits;
@@ -911,7 +915,12 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
 #define B200Q_HG_LAUNCH(BF, PS)                                                                   \
     hessian_gemm_kernel<BF, PS><<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(                        \
         tmap, gemm_out, K, T, tokens_per_split, tiles_n, norms, kb_per_sample)
-    const bool chunked = per_sample || kblocks / splits > kb_per_sample;   // long k loops only
+    // (B200Q_HESSIAN_CHUNKED=0 keeps one long accumulation for A/B timing; per-sample always chunks)
+    static const bool chunk_env = []() {
+      const char* e = std::getenv("B200Q_HESSIAN_CHUNKED");
+      return !(e != nullptr && e[0] == '0');
+    }();
+    const bool chunked = per_sample || (chunk_env && kblocks / splits > kb_per_sample);   // long k loops only
     if (chunked) {
       if (bf16_ops) B200Q_HG_LAUNCH(true, true); else B200Q_HG_LAUNCH(false, true);
     } else {

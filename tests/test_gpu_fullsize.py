@@ -101,7 +101,13 @@ def test_hessian_and_gram_at_llama_token_counts():
     half = n // 2 * rows
     G_two = T.hessian_accum(X[half:], rows, T.hessian_accum(X[:half], rows, normalize=False),
                             normalize=False)
-    assert ((G_all - G_two).abs().max() / G_all.abs().max()).item() < 1e-5
+    # The tensor core truncates every product at the accumulator's ulp, so a same-sign sum (the
+    # diagonal) comes out low by ~N * 2^-24 per accumulation chain; the kernel folds 4096-token
+    # chunks into a round-to-nearest running total, which bounds that at 2.4e-4 (one long chain of
+    # 37k tokens measured 2.3e-3 low, and the two ways of splitting the samples 4.4e-4 apart).
+    assert ((G_all - G_two).abs().max() / G_all.abs().max()).item() < 3e-4
+    exact_diag = (X[:, :8].double() ** 2).sum(0)
+    assert ((torch.diag(G_all)[:8].double() - exact_diag).abs() / exact_diag).max().item() < 4e-4
     assert torch.equal(G_all, G_all.T)
     # normalised Hessian: every sample has trace 1 (up to the 1e-5 in the denominator)
     H, norms = T.hessian_accum(X, rows, return_norms=True)
