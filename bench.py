@@ -61,13 +61,13 @@ W_BIT, GROUP = 4, 128
 N_CALIB, CALIB_TOKENS = 128, 2048        # calibration batches x tokens per batch
 N_GRID = 20
 DTYPES = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
-METHODS = ("awq", "awq_fixed", "gptq", "gptq_fast", "pot", "apot", "smoothquant")
+METHODS = ("awq", "awq_fixed", "gptq", "gptq_fast", "pot", "apot", "smoothquant", "smoothquant_search")
 NEEDS_ACTS = ("awq", "gptq")
 # dominant C-ABI entry point per method: (name, bound)
 DOMINANT = {"awq": ("hessian_gemm", "tensor"), "gptq": ("hessian_gemm", "tensor"),
             "awq_fixed": ("group_fakequant", "hbm"), "gptq_fast": ("gptq_parity_quant", "hbm"),
             "smoothquant": ("group_fakequant", "hbm"), "pot": ("pot_quant", "hbm"),
-            "apot": ("apot_quant", "hbm")}
+            "apot": ("apot_quant", "hbm"), "smoothquant_search": ("smooth_alpha_errors", "hbm")}
 
 
 def layer_list(model: str):
@@ -186,6 +186,16 @@ def make_step(method: str, acts_by_K, stats_by_K, act_scale_by_K):
     if method == "smoothquant":
         return lambda model: smooth_quant_quantizer.smoothquant_quantize_model_weight(
             model, 8, GROUP, by_layer(model, act_scale_by_K), alpha=0.5, verbose=False)
+    if method == "smoothquant_search":
+        def step(model):
+            # (a18) 20-point alpha sweep, (a17) smooth + quantize with the winner
+            scales = by_layer(model, act_scale_by_K)
+            alpha = smooth_quant_quantizer.smoothquant_search_alpha(model, [], scales, 8, GROUP,
+                                                                    n_grid=N_GRID, verbose=False)
+            smooth_quant_quantizer.smoothquant_quantize_model_weight(model, 8, GROUP, scales,
+                                                                     alpha=alpha, verbose=False)
+            return alpha
+        return step
     raise SystemExit(f"unknown method {method}")
 
 
@@ -200,7 +210,8 @@ def cpu_baseline(method: str, model: str, dtype, tokens_total: int, budget_s: fl
     per = budget_s / len(shapes)
     total_s, total_rows, notes = 0.0, 0, []
     for name, N, K, count in shapes:
-        elem_cost = {"pot": 2e-6, "apot": 1.4e-6}.get(method, 2e-8 if method != "awq" else 6e-7)
+        elem_cost = {"pot": 2e-6, "apot": 1.4e-6, "smoothquant_search": 5e-7}.get(
+            method, 2e-8 if method != "awq" else 6e-7)
         rows = N if elem_cost * N * K <= per else max(64, int(per / (elem_cost * K)) // 64 * 64)
         rows = min(rows, N)
         w = (torch.randn(rows, K, generator=g) * 0.02).to(dtype)
@@ -244,6 +255,11 @@ def cpu_baseline(method: str, model: str, dtype, tokens_total: int, budget_s: fl
             O.apot_quant(w, W_BIT, GROUP, 2, total_elements=N * K)
         elif method == "smoothquant":
             O.smoothquant_layer(w, act, 0.5, 8, GROUP)
+        elif method == "smoothquant_search":
+            alphas = torch.linspace(0, 1, N_GRID, dtype=torch.float64).tolist()
+            S = torch.stack([O.smooth_scale(act.clamp(min=1e-5), w, a).float() for a in alphas])
+            errs = O.smooth_alpha_errors(w, S.to(w.dtype).float(), act, 8, GROUP)
+            O.smoothquant_layer(w, act, alphas[int(torch.argmin(errs))], 8, GROUP)
         dt = (time.perf_counter() - t0) * (N / rows) + extra
         total_s += dt * count
         total_rows += N * count
@@ -280,7 +296,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     dtype = DTYPES[args.dtype]
     tokens_total = args.calib_batches * args.calib_tokens
-    bits = 8 if args.method == "smoothquant" else W_BIT
+    bits = 8 if args.method.startswith("smoothquant") else W_BIT
     what = {"awq": f"AWQ w{bits} g{GROUP} with the {N_GRID}-point scale grid search "
                    f"(activation stats + Gram matrix + candidate losses + quantize), "
                    f"{args.calib_batches} x {args.calib_tokens}-token calibration activations (bf16)",
@@ -290,7 +306,9 @@ def main():
             "gptq_fast": f"GPTQ w{bits}, reference-parity column stage only (H, H^-1 cannot reach the output)",
             "pot": f"POT w{bits} g{GROUP}, 200-point scale search",
             "apot": f"APOT w{bits} g{GROUP} k2, 20-point scale search",
-            "smoothquant": f"SmoothQuant w{bits} g{GROUP} alpha 0.5"}[args.method]
+            "smoothquant": f"SmoothQuant w{bits} g{GROUP} alpha 0.5",
+            "smoothquant_search": f"SmoothQuant w{bits} g{GROUP} with the {N_GRID}-point alpha sweep "
+                                  f"(reconstruction error per alpha + smooth + quantize)"}[args.method]
     workload = f"{args.model}-shape {what}; every nn.Linear incl. lm_head, random-init {args.dtype} weights"
     total_rows = sum(N * c for _, N, _, c in MODELS[args.model])
     total_elems = sum(N * K * c for _, N, K, c in MODELS[args.model])
@@ -400,7 +418,7 @@ def main():
     kq = {n: _lib.profile_query(n) for n in
           ("hessian_gemm", "hessian_prescale", "hessian_reduce", "awq_search_gemm", "awq_search_delta", "awq_search_fold",
            "act_meanabs", "group_fakequant", "gptq_parity_quant", "col_absmax", "spd_inverse",
-           "pot_quant", "apot_quant", "seq_sum_rows")}
+           "pot_quant", "apot_quant", "seq_sum_rows", "smooth_alpha_errors", "smooth_scale")}
     kall = _lib.profile_query(None)
 
     t = torch.tensor([ms_total], dtype=torch.float64, device=device)

@@ -90,9 +90,11 @@ def _scale_activations_hook(mod: nn.Module, inputs):
     return (x,) + tuple(inputs[1:]) if isinstance(inputs, tuple) else (x,)
 
 
-def _layer_smoothing_scale(W: torch.Tensor, act_scale: torch.Tensor, alpha: float):
-    """(s as fp32 on W's device, dtype s has in torch's promotion rules)."""
-    colmax = _dist.allreduce_max(_ops.col_absmax(W))
+def _layer_smoothing_scale(W: torch.Tensor, act_scale: torch.Tensor, alpha: float, colmax=None):
+    """(s as fp32 on W's device, dtype s has in torch's promotion rules).  `colmax` = the column
+    |max| of W over all row shards when the caller already has it (the alpha sweep)."""
+    if colmax is None:
+        colmax = _dist.allreduce_max(_ops.col_absmax(W))
     s = _ops.smooth_scale(act_scale, colmax, alpha, act_scale.dtype if act_scale.dtype in
                           _ops.DTYPE_CODE else torch.float32, W.dtype)
     return s, torch.promote_types(act_scale.dtype, W.dtype)
@@ -218,7 +220,8 @@ def smoothquant_search_alpha(model: nn.Module, calib_samples: List[torch.Tensor]
             a = act_scales[name].to(W.device, torch.float32).clamp(min=1e-5)
             # one smoothing-scale vector per alpha ([n_grid, K], tiny), then ONE kernel sweeps all
             # alphas over the weight: W is read once, the errors accumulate on the device
-            scales = [_layer_smoothing_scale(W, act_scales[name], alpha) for alpha in alphas]
+            colmax = _dist.allreduce_max(_ops.col_absmax(W))
+            scales = [_layer_smoothing_scale(W, act_scales[name], alpha, colmax) for alpha in alphas]
             S = torch.stack([s for s, _ in scales])
             totals = _ops.smooth_alpha_errors(W.to(scales[0][1]), S, a, w_bit, q_group_size, totals)
         if totals is not None:
