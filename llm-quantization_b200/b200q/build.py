@@ -55,6 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     headers = list(CSRC.glob("*.cuh")) + [REPO / "include" / "b200quant.h"]
     objs = []
     log_lines = []
+    jobs = []
     for name, extra in SOURCES.items():
         src = CSRC / name
         if not src.exists():
@@ -62,16 +63,20 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         obj = OBJ_DIR / (src.stem + ".o")
         objs.append(obj)
         if force or _stale(obj, [src, *headers]):
-            cmd = [nvcc, *ARCH, *COMMON, *extra, "-I", str(REPO / "include"), "-c", str(src),
-                   "-o", str(obj)]
-            res = subprocess.run(cmd, capture_output=True, text=True)
-            log_lines.append("$ " + " ".join(cmd))
-            log_lines.append(res.stderr)
-            if res.returncode != 0:
-                sys.stderr.write(res.stdout + res.stderr)
-                raise RuntimeError(f"nvcc failed on {name}")
-            if verbose:
-                print(res.stderr)
+            jobs.append((name, [nvcc, *ARCH, *COMMON, *extra, "-I", str(REPO / "include"), "-c",
+                                str(src), "-o", str(obj)]))
+    # the translation units are independent: compile them side by side
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
+        results = list(pool.map(lambda j: subprocess.run(j[1], capture_output=True, text=True), jobs))
+    for (name, cmd), res in zip(jobs, results):
+        log_lines.append("$ " + " ".join(cmd))
+        log_lines.append(res.stderr)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError(f"nvcc failed on {name}")
+        if verbose:
+            print(res.stderr)
     if force or _stale(LIB_PATH, objs):
         cmd = [nvcc, *ARCH, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-lcudart"]
         res = subprocess.run(cmd, capture_output=True, text=True)
