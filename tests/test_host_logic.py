@@ -155,3 +155,28 @@ def test_gptq_group_dealing_balances_the_inverse_work():
     assert max(load) <= sum(load) / 8 + 11008.0 ** 3
     assert owner == gq._deal_layers(list(reversed(layers)), 8), "assignment must not depend on order"
     assert gq._deal_layers(layers, 1) == {n: 0 for n, _ in layers}
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs on the host only (the oracle port) and must print exactly one
+    JSON line carrying the contract's keys -- checked here on the tiny model so it takes seconds."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    repo = Path(__file__).resolve().parent.parent
+    res = subprocess.run([sys.executable, str(repo / "bench.py"), "--impl", "reference", "--model", "tiny",
+                          "--method", "awq_fixed", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=str(repo))
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["gpu_launches"] == 0
+    for key in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"):
+        assert key in d, key
+    assert d["vs_baseline"] is None and d["higher_is_better"] is True
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert "workload" in d["config"]
