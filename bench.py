@@ -553,7 +553,9 @@ def main():
         fr = sum(N * K * K * tri_fraction(K) for _, N, K in layers) / wsum
         stages["awq_search_gemm"]["executed_mma_fraction"] = fr
         stages["awq_search_gemm"]["executed_tflops"] = stages["awq_search_gemm"]["tflops"] * fr
-    cpu = None if args.no_cpu_baseline else cpu_baseline(args.method, args.model, dtype, tokens_total)
+    # the CPU baseline is a rank-0, single-GPU-run figure (the host cores are shared by all ranks)
+    cpu = None if (args.no_cpu_baseline or world > 1 or rank != 0) else \
+        cpu_baseline(args.method, args.model, dtype, tokens_total)
     line = {
         "metric": metric, "value": total_rows / (ms_step * 1e-3), "unit": "rows/s",
         "seconds": ms_step * 1e-3, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
