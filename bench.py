@@ -278,7 +278,11 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--method", default="awq", choices=METHODS)
-    ap.add_argument("--model", default="llama2-7b", choices=sorted(MODELS))
+    ap.add_argument("--model", default="llama2-7b",
+                    help="one of " + ", ".join(sorted(MODELS)) + ", or matrix-NxK for a single Linear "
+                         "(BASELINE configs[4]: the 4096x4096 ... 28672x8192 sweep)")
+    ap.add_argument("--bits", type=int, default=W_BIT, choices=[2, 3, 4, 8],
+                    help="weight bits of the GPTQ / AWQ / POT / APOT methods (BASELINE configs[2]: w3, w4)")
     ap.add_argument("--dtype", default="f32", choices=sorted(DTYPES))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--calib-batches", type=int, default=N_CALIB)
@@ -286,6 +290,17 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.model.startswith("matrix-"):
+        try:
+            n_, k_ = (int(v) for v in args.model[len("matrix-"):].lower().split("x"))
+        except ValueError:
+            ap.error("--model matrix-NxK needs two integers, e.g. matrix-28672x8192")
+        if n_ <= 0 or k_ <= 0 or k_ % GROUP:
+            ap.error(f"--model matrix-NxK: K must be a positive multiple of {GROUP}")
+        MODELS[args.model] = [("matrix", n_, k_, 1)]
+    elif args.model not in MODELS:
+        ap.error(f"unknown --model {args.model}")
+    globals()["W_BIT"] = args.bits
     # the contract is ONE JSON line on stdout: progress text of the entry points (the reference's
     # functions print, e.g. "Searching for optimal scale factor...") goes to stderr
     out = sys.stdout
