@@ -575,11 +575,12 @@ smooth_alpha_err_kernel(const T* __restrict__ W, const float* __restrict__ S,
   __syncwarp();
   for (int64_t g = warp; g < n_groups; g += nwarps) {
     const int64_t off = g * G;
+    const int64_t k0 = off % K;                        // a group never crosses a row (G divides K)
     for (int a = 0; a < n_alpha; ++a) {                // the group stays in L1 across the alphas
-      const float* sa = S + (int64_t)a * K;
+      const float* sa = S + (int64_t)a * K + k0;
       float mx = -INFINITY, mn = INFINITY;
       for (int64_t i = lane; i < G; i += 32) {
-        const float x = ST<T>::rnd(__fdiv_rn(to_f(W[off + i]), sa[(off + i) % K]));
+        const float x = ST<T>::rnd(__fdiv_rn(to_f(W[off + i]), sa[i]));
         mx = fmaxf(mx, x); mn = fminf(mn, x);
       }
 #pragma unroll
@@ -591,16 +592,96 @@ smooth_alpha_err_kernel(const T* __restrict__ W, const float* __restrict__ S,
       group_params<T, false>(mx, mn, maxint, scale, zp);
       float e2 = 0.f;
       for (int64_t i = lane; i < G; i += 32) {
-        const int64_t k = (off + i) % K;
         const float w = to_f(W[off + i]);
-        const float sv = sa[k];
+        const float sv = sa[i];
         const float x = ST<T>::rnd(__fdiv_rn(w, sv));
         const float code = clampf(ST<T>::rnd(rint_then_clamped(ST<T>::rnd(__fdiv_rn(x, scale))) + zp),
                                   0.f, maxint);
         const float deq = ST<T>::rnd(ST<T>::rnd(code - zp) * scale);
-        const float e = (ST<T>::rnd(deq * sv) - w) * act[k];
+        const float e = (ST<T>::rnd(deq * sv) - w) * act[k0 + i];
         e2 = fmaf(e, e, e2);
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+      if (lane == 0) accs[wib][a] += (double)e2;
+    }
+  }
+  __syncwarp();
+  if (lane < n_alpha) partial[(int64_t)lane * nwarps + warp] = accs[wib][lane];
+}
+
+// G == 128: the register form of group128_kernel -- eight lanes own a group (16 elements per lane,
+// loaded once with 128-bit accesses and kept in registers across all alphas), a warp works on four
+// consecutive groups.  Same arithmetic per element as the generic kernel above.
+template <typename T>
+__global__ void __launch_bounds__(256)
+smooth_alpha_err128_kernel(const T* __restrict__ W, const float* __restrict__ S,
+                           const float* __restrict__ act, int64_t n_groups, int64_t K, float maxint,
+                           int n_alpha, double* __restrict__ partial) {
+  constexpr int VEC = ST<T>::VEC;
+  constexpr int NV = 16 / VEC;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int l8 = lane & 7, sub = lane >> 3;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t groups_per_row = K / 128;
+  __shared__ double accs[8][32];
+  if (lane < n_alpha) accs[wib][lane] = 0.0;
+  __syncwarp();
+  for (int64_t base = warp * 4; base < n_groups; base += nwarps * 4) {
+    const int64_t g = base + sub;
+    const bool valid = g < n_groups;
+    const int64_t gg = valid ? g : n_groups - 1;
+    const T* wp = W + gg * 128 + l8 * VEC;
+    const int64_t c0 = (gg % groups_per_row) * 128 + l8 * VEC;
+    float w[16], aw[16];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float t[VEC];
+      load_vec<T>(wp + i * 8 * VEC, t);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) w[i * VEC + j] = t[j];
+#pragma unroll
+      for (int j = 0; j < VEC; j += 4) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(act + c0 + i * 8 * VEC + j));
+        aw[i * VEC + j] = f.x; aw[i * VEC + j + 1] = f.y;
+        aw[i * VEC + j + 2] = f.z; aw[i * VEC + j + 3] = f.w;
+      }
+    }
+    for (int a = 0; a < n_alpha; ++a) {
+      const float* sa = S + (int64_t)a * K + c0;
+      float sv[16], x[16];
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < VEC; j += 4) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(sa + i * 8 * VEC + j));
+          sv[i * VEC + j] = f.x; sv[i * VEC + j + 1] = f.y;
+          sv[i * VEC + j + 2] = f.z; sv[i * VEC + j + 3] = f.w;
+        }
+      float mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        x[e] = ST<T>::rnd(__fdiv_rn(w[e], sv[e]));
+        mx = fmaxf(mx, x[e]); mn = fminf(mn, x[e]);
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      }
+      float scale, zp;
+      group_params<T, false>(mx, mn, maxint, scale, zp);
+      const Divisor sd(scale);
+      float e2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float code = clampf(ST<T>::rnd(rint_then_clamped(ST<T>::rnd(sd.div(x[e]))) + zp), 0.f, maxint);
+        const float deq = ST<T>::rnd(ST<T>::rnd(code - zp) * scale);
+        const float err = (ST<T>::rnd(deq * sv[e]) - w[e]) * aw[e];
+        e2 = fmaf(err, err, e2);
+      }
+      if (!valid) e2 = 0.f;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
       if (lane == 0) accs[wib][a] += (double)e2;
@@ -1289,10 +1370,18 @@ int b200q_smooth_alpha_errors(const void* W, int64_t N, int64_t K, int64_t group
   double* partial = static_cast<double*>(work);
   KernelScope scope("smooth_alpha_errors", (double)N * K * elem_size(dtype), 0, st);
   const float maxint = (float)((1 << n_bit) - 1);
-  B200Q_DISPATCH_DTYPE(dtype, T,
-                       (smooth_alpha_err_kernel<T><<<blocks, 256, 0, st>>>(
-                           static_cast<const T*>(W), S, act_weight, n_groups, G, K, maxint, n_alpha,
-                           partial)));
+  const bool fast128 = G == 128 && aligned16(W) && aligned16(S) && aligned16(act_weight) && K % 4 == 0;
+  if (fast128) {
+    B200Q_DISPATCH_DTYPE(dtype, T,
+                         (smooth_alpha_err128_kernel<T><<<blocks, 256, 0, st>>>(
+                             static_cast<const T*>(W), S, act_weight, n_groups, K, maxint, n_alpha,
+                             partial)));
+  } else {
+    B200Q_DISPATCH_DTYPE(dtype, T,
+                         (smooth_alpha_err_kernel<T><<<blocks, 256, 0, st>>>(
+                             static_cast<const T*>(W), S, act_weight, n_groups, G, K, maxint, n_alpha,
+                             partial)));
+  }
   smooth_alpha_reduce_kernel<<<n_alpha, 256, 0, st>>>(partial, nwarps, n_alpha, err, accumulate);
   count_launch(2);
   return check_launch("smooth_alpha_errors");
