@@ -94,3 +94,42 @@ def dequantize(record: Dict) -> torch.Tensor:
     else:
         raise ValueError(f"unknown scheme {record['scheme']!r}")
     return w.reshape(shape)
+
+
+# --------------------------------------------------------------------------------------------------
+# model level: one record per nn.Linear, one file per model
+# --------------------------------------------------------------------------------------------------
+FORMAT_VERSION = 1
+
+
+def export_model(model, n_bit: int, group: int, scheme: str = "uniform_asym") -> Dict[str, Dict]:
+    """{module name: record} for every nn.Linear of `model` (weights may live on the host; they are
+    streamed through the GPU).  scheme: "uniform_asym" (pseudo_quantize_tensor) or
+    "gptq_column_sym" (the reference's GPTQ column stage)."""
+    import torch.nn as nn
+    fn = {"uniform_asym": lambda w: export_uniform(w, n_bit, group),
+          "gptq_column_sym": lambda w: export_gptq_parity(w, n_bit)}.get(scheme)
+    if fn is None:
+        raise ValueError(f"unknown scheme {scheme!r}")
+    return {name: fn(m.weight.data) for name, m in model.named_modules() if isinstance(m, nn.Linear)}
+
+
+def save_records(path, records: Dict[str, Dict]) -> None:
+    """Write {name: record} to `path` (torch.save of plain host tensors and ints)."""
+    host = {name: {k: (v.detach().cpu() if isinstance(v, torch.Tensor) else v) for k, v in rec.items()}
+            for name, rec in records.items()}
+    torch.save({"format": "b200q-packed", "version": FORMAT_VERSION, "records": host}, path)
+
+
+def load_records(path, device=None) -> Dict[str, Dict]:
+    """Read a file written by save_records; tensors go to `device` when given."""
+    blob = torch.load(path, map_location="cpu", weights_only=True)
+    if not isinstance(blob, dict) or blob.get("format") != "b200q-packed":
+        raise ValueError(f"{path}: not a b200q packed-weights file")
+    if blob.get("version") != FORMAT_VERSION:
+        raise ValueError(f"{path}: format version {blob.get('version')} (this build reads {FORMAT_VERSION})")
+    records = blob["records"]
+    if device is not None:
+        records = {name: {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in rec.items()}
+                   for name, rec in records.items()}
+    return records

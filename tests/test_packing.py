@@ -60,3 +60,23 @@ def test_gptq_export_round_trips(dtype):
     rec = E.export_gptq_parity(W, 4)
     assert rec["bits"] == 5
     assert torch.equal(E.dequantize(rec), ops.gptq_parity_quant(W, 4))
+
+
+def test_records_file_round_trip(tmp_path):
+    """save_records / load_records keep every field of a record (host-only: no kernels involved)."""
+    from b200q import export as E
+    rec = {"scheme": "uniform_asym", "bits": 4, "group": 128, "shape": (8, 256), "dtype": "float16",
+           "qweight": torch.randint(-2 ** 31, 2 ** 31 - 1, (8, 32), dtype=torch.int32),
+           "scales": torch.rand(16), "zeros": torch.randint(0, 16, (16,)).float()}
+    path = tmp_path / "model.b200q"
+    E.save_records(path, {"layers.0.q_proj": rec})
+    back = E.load_records(path)
+    assert set(back) == {"layers.0.q_proj"}
+    got = back["layers.0.q_proj"]
+    assert got["scheme"] == "uniform_asym" and got["bits"] == 4 and tuple(got["shape"]) == (8, 256)
+    for k in ("qweight", "scales", "zeros"):
+        assert torch.equal(got[k], rec[k])
+    (tmp_path / "other.pt").write_bytes(b"")
+    torch.save({"format": "something else"}, tmp_path / "other.pt")
+    with pytest.raises(ValueError):
+        E.load_records(tmp_path / "other.pt")
