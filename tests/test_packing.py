@@ -80,3 +80,20 @@ def test_records_file_round_trip(tmp_path):
     torch.save({"format": "something else"}, tmp_path / "other.pt")
     with pytest.raises(ValueError):
         E.load_records(tmp_path / "other.pt")
+
+
+@pytest.mark.gpu
+def test_export_model_file_round_trip_dequantizes_to_the_quantizer_output(tmp_path):
+    import torch.nn as nn
+    import copy
+    from b200q import export as E
+    from quantization_utils import pseudo_quantize_tensor
+    torch.manual_seed(3)
+    net = nn.Sequential(nn.Linear(256, 128, bias=False), nn.ReLU(), nn.Linear(128, 384, bias=False))
+    records = E.export_model(net, 4, 128)                   # host-resident weights
+    assert set(records) == {"0", "2"}
+    E.save_records(tmp_path / "net.b200q", records)
+    loaded = E.load_records(tmp_path / "net.b200q", device="cuda")
+    for name, lin in (("0", net[0]), ("2", net[2])):
+        want = pseudo_quantize_tensor(lin.weight.data.clone(), 4, 128)
+        assert torch.equal(E.dequantize(loaded[name]).cpu(), want.cpu())
