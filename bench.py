@@ -352,7 +352,7 @@ def main():
     import torch.distributed as td
     if world > 1:
         td.init_process_group("nccl", device_id=device)
-    from b200q import _lib, ops, dist as bdist, pipeline, tensor_ops
+    from b200q import _lib, ops, dist as bdist
 
     layers = layer_list(args.model)
     model = ShapeModel()

@@ -8,7 +8,7 @@ tensor-level functions) — the arithmetic still runs on the GPU.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 

@@ -16,7 +16,6 @@ from __future__ import annotations
 import itertools
 import sys
 from pathlib import Path
-from typing import List, Tuple
 
 import torch
 import torch.nn as nn

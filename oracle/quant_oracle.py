@@ -18,7 +18,7 @@ reference would for the given dtype (they are torch programs, not re-derivations
 from __future__ import annotations
 
 import itertools
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, Optional, Sequence
 
 import torch
 
