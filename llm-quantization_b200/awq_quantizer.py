@@ -127,13 +127,25 @@ def awq_search_scale_factor(
     index = {n: i for i, (n, _) in enumerate(items)}
     grams = {}
 
+    def supported(K: int) -> bool:
+        # TMA needs a 16-byte row pitch (K % 8); a quantisation group must divide the row
+        return K % 8 == 0 and not (0 < q_group_size < K and K % q_group_size != 0)
+
     def start_gram(i, device):
         n, m = items[i]
-        grams[n] = _tops.gram_matrix_begin(input_feat[n], m.weight.shape[1], device)
+        if supported(m.weight.shape[1]):
+            grams[n] = _tops.gram_matrix_begin(input_feat[n], m.weight.shape[1], device)
+
+    skipped = []
 
     def compute(name, _module, W):
         K = W.shape[1]
         feats = input_feat[name]
+        # Shapes the kernels cannot take do not raise here: the reference's search returns a float for ANY model
+        # (awq_quantizer.py:88-126), so such a layer is left out of the total with a warning.
+        if not supported(K):
+            skipped.append(name)
+            return None
         # 2-D [tokens, K] features are raw activations: their per-batch mean|x| is the statistic
         # the quantizer ranks channels by (quantization_utils.py:231); 1-D features already are it
         from b200q.streaming import ActivationStream
@@ -154,7 +166,9 @@ def awq_search_scale_factor(
         # the row count instead of rescaling the [K, K] matrix
         gram = grams.pop(name)
         H = _tops.gram_matrix_end(gram, normalise=False)
-        loss = _tops.awq_search_losses(W, H, mask, w_bit, q_group_size, candidates)
+        # (the kernel takes up to 32 candidates per call: longer grids go in slices)
+        loss = torch.cat([_tops.awq_search_losses(W, H, mask, w_bit, q_group_size, candidates[c:c + 32])
+                          for c in range(0, len(candidates), 32)])
         loss.mul_(1.0 / gram.rows_total)
         if totals:
             totals[0] += loss
@@ -164,6 +178,10 @@ def awq_search_scale_factor(
 
     # host-resident weights are prefetched one layer ahead; nothing is written back
     _pipeline.run_layers(items, compute)
+    if skipped:
+        import warnings
+        warnings.warn(f"awq_search_scale_factor: {len(skipped)} layer(s) left out of the search "
+                      f"(in_features not a multiple of 8 or of the group size): {skipped[:4]}")
     if not totals:
         best = (lo + hi) / 2.0
     else:

@@ -88,6 +88,39 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+REFERENCE_SRC = Path("/root/reference")
+REFERENCE_STAGE = REPO / "baseline" / "_ref"
+
+
+def stage_reference() -> Path | None:
+    """Copy the UNMODIFIED reference modules (flat *.py + config.json) from /root/reference into the
+    git-ignored baseline/_ref/, so that they travel to the GPU box with the snapshot.  Used there
+    only (a) to run the reference's own test_quantization.py against the drop-in modules and (b) as
+    the timed CPU implementation of `bench.py --impl reference`.  Nothing in the product imports it
+    except the documented out-of-scope pass-throughs of quantization_utils (HF load / perplexity).
+    Returns the staged directory, or None when no reference checkout is present (GPU box: the
+    files staged earlier are used as they are)."""
+    if not REFERENCE_SRC.is_dir():
+        return REFERENCE_STAGE if (REFERENCE_STAGE / "test_quantization.py").exists() else None
+    REFERENCE_STAGE.mkdir(parents=True, exist_ok=True)
+    for src in sorted(REFERENCE_SRC.glob("*.py")) + [REFERENCE_SRC / "config.json"]:
+        if src.exists():
+            dst = REFERENCE_STAGE / src.name
+            if not dst.exists() or dst.read_bytes() != src.read_bytes():
+                shutil.copyfile(src, dst)
+    return REFERENCE_STAGE
+
+
+def reference_dir() -> Path | None:
+    """Where an unmodified reference checkout can be imported from: $LLMQ_REFERENCE_DIR when set
+    (authoritative), else /root/reference, else the staged baseline/_ref."""
+    env = os.environ.get("LLMQ_REFERENCE_DIR")
+    for cand in ((env,) if env else (REFERENCE_SRC, REFERENCE_STAGE)):
+        if cand and (Path(cand) / "quantization_utils.py").exists():
+            return Path(cand)
+    return None
+
+
 if __name__ == "__main__":
     p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(p)

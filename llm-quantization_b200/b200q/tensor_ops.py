@@ -61,25 +61,36 @@ def hessian_finalize(H: torch.Tensor, scale: float, damp: float) -> torch.Tensor
     return H
 
 
+class FactorizationError(_lib.B200QuantError):
+    """The matrix handed to spd_inverse was not positive definite (a Cholesky pivot <= 0)."""
+
+
 def spd_inverse(H: torch.Tensor, ridge: float = 0.0, want_inverse: bool = True,
-                want_upper: bool = False, owner: int = 0, broadcast: bool = True):
+                want_upper: bool = False, owner: int = 0, broadcast: bool = True,
+                check: bool = True, return_info: bool = False):
     """inv(H + ridge I) (and/or the upper Cholesky factor U of it, U^T U = inverse) for a CUDA
     fp32 SPD matrix.  Returns Hinv, U or (Hinv, U).  Under row sharding rank `owner` computes and
     the result is broadcast (the inverse is shared by all row shards); with broadcast=False the
     other ranks get an uninitialised buffer and the caller broadcasts later, which lets different
-    ranks invert different layers' matrices at the same time."""
+    ranks invert different layers' matrices at the same time.
+
+    The kernels report a non-positive pivot through a device flag (0 = ok, j = pivot of column j).
+    check=True reads it (one host sync) and raises FactorizationError -- on every rank under
+    sharding -- instead of handing back garbage; check=False leaves that to the caller, who gets
+    the int32 flag tensor with return_info=True (the model walker checks a whole group of layers
+    with one sync)."""
     assert H.is_cuda and H.dtype == torch.float32 and H.dim() == 2 and H.shape[0] == H.shape[1]
     K = H.shape[0]
     lib = _lib.load()
     Hinv = torch.empty_like(H) if want_inverse else None
     U = torch.empty_like(H) if want_upper else None
+    info = torch.zeros(1, dtype=torch.int32, device=H.device)
     if not _dist.is_sharded() or _dist.rank() == owner:
         A = H.contiguous()
         if ridge != 0.0:
             A = hessian_finalize(A.clone(), 1.0, ridge)
         with _on(H.device):
             work = _workspace(H.device, lib.b200q_spd_inverse_workspace(K))
-            info = torch.zeros(1, dtype=torch.int32, device=H.device)
             rc = lib.b200q_spd_inverse(A.data_ptr(), None if Hinv is None else Hinv.data_ptr(),
                                        None if U is None else U.data_ptr(), K, work.data_ptr(),
                                        info.data_ptr(), _stream())
@@ -88,18 +99,31 @@ def spd_inverse(H: torch.Tensor, ridge: float = 0.0, want_inverse: bool = True,
         for t in (Hinv, U):
             if t is not None:
                 _dist.broadcast(t, owner)
-    if Hinv is not None and U is not None:
-        return Hinv, U
-    return Hinv if Hinv is not None else U
+        if check or return_info:
+            _dist.broadcast(info, owner)
+    if check:
+        raise_if_not_spd(info, K)
+    out = (Hinv, U) if (Hinv is not None and U is not None) else (Hinv if Hinv is not None else U)
+    return (out, info) if return_info else out
+
+
+def raise_if_not_spd(info, K: int, what: str = "spd_inverse") -> None:
+    """info: the device flag of spd_inverse (or its int value)."""
+    j = int(info.item()) if isinstance(info, torch.Tensor) else int(info)
+    if j != 0:
+        raise FactorizationError(
+            f"{what}: the {K} x {K} matrix is not positive definite (pivot {j} <= 0); the reference "
+            f"would fall back to torch.linalg.pinv here (gptq_quantizer.py:161-165) -- raise the "
+            f"damping (perp_damp) instead")
 
 
 def compensation_factor(H: torch.Tensor, perm: Optional[torch.Tensor] = None, owner: int = 0,
-                        broadcast: bool = True) -> torch.Tensor:
+                        broadcast: bool = True, check: bool = True, return_info: bool = False):
     """U = chol(inv(H_perm + 1e-6 I), upper): what the compensated column loop multiplies by."""
     if perm is not None:
         H = H[perm][:, perm]
     return spd_inverse(H.contiguous(), ridge=1e-6, want_inverse=False, want_upper=True, owner=owner,
-                       broadcast=broadcast)
+                       broadcast=broadcast, check=check, return_info=return_info)
 
 
 def gptq_compensated(W: torch.Tensor, H: Optional[torch.Tensor], n_bit: int, group: int,

@@ -259,8 +259,8 @@ inline int elem_size(int dtype) { return dtype == B200Q_F32 ? 4 : 2; }
 
 // elementwise.cu: dW_c = Q_c(W) - W (bf16) for all AWQ search candidates; D + c * cand_stride
 int launch_awq_delta(const void* W, void* D, const uint8_t* salient, int64_t N, int64_t K,
-                     int64_t cand_stride, int n_bit, const float* sf_host, int n_cand, int dtype,
-                     cudaStream_t st);
+                     int64_t group, int64_t cand_stride, int n_bit, const float* sf_host, int n_cand,
+                     int dtype, cudaStream_t st);
 
 // host tables of torch-CPU log2 semantics (log2_tables.cpp)
 const uint32_t* log2_round_thresholds(int dtype);  // index e+127, e in [-127,127]

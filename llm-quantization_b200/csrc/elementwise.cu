@@ -528,11 +528,53 @@ awq_delta128_kernel(const T* __restrict__ W, __nv_bfloat16* __restrict__ D,
   }
 }
 
+// Any group length (32, 64, 256, per-row ...): one warp per group, and per candidate a min/max pass
+// and a quantize pass over the group (re-read through L1/L2; W itself comes from HBM once).  IEEE
+// divisions throughout -- this is the boundary-completeness path, not the measured one.
+template <typename T>
+__global__ void __launch_bounds__(256)
+awq_delta_generic_kernel(const T* __restrict__ W, __nv_bfloat16* __restrict__ D,
+                         const uint8_t* __restrict__ salient, int64_t n_groups, int64_t G, int64_t K,
+                         int64_t cand_stride, float maxint, CandParam cp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t g = warp; g < n_groups; g += nwarps) {
+    const int64_t off = g * G;
+    for (int c = 0; c < cp.n; ++c) {
+      const float sf = cp.sf[c];
+      float mx = -INFINITY, mn = INFINITY;
+      for (int64_t i = lane; i < G; i += 32) {
+        const float w = to_f(W[off + i]);
+        const float x = salient[(off + i) % K] ? ST<T>::rnd(w * sf) : w;     // awq_quantizer.py:70
+        mx = fmaxf(mx, x); mn = fminf(mn, x);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      }
+      float scale, zp;
+      group_params<T, false>(mx, mn, maxint, scale, zp);
+      for (int64_t i = lane; i < G; i += 32) {
+        const float w = to_f(W[off + i]);
+        const bool s = salient[(off + i) % K] != 0;
+        const float x = s ? ST<T>::rnd(w * sf) : w;
+        const float code = clampf(ST<T>::rnd(rintf(ST<T>::rnd(__fdiv_rn(x, scale))) + zp), 0.f, maxint);
+        float o = ST<T>::rnd(ST<T>::rnd(code - zp) * scale);
+        if (s) o = ST<T>::rnd(__fdiv_rn(o, sf));                               // awq_quantizer.py:81
+        D[c * cand_stride + off + i] = __float2bfloat16_rn(o - w);
+      }
+    }
+  }
+}
+
 int launch_awq_delta(const void* W, void* D, const uint8_t* salient, int64_t N, int64_t K,
-                     int64_t cand_stride, int n_bit, const float* sf_host, int n_cand, int dtype,
-                     cudaStream_t st) {
-  B200Q_REQUIRE(K % 128 == 0, "awq_search: in_features must be a multiple of 128 (group size)");
-  B200Q_REQUIRE(n_cand >= 1 && n_cand <= 32, "awq_search: 1..32 candidates");
+                     int64_t group, int64_t cand_stride, int n_bit, const float* sf_host, int n_cand,
+                     int dtype, cudaStream_t st) {
+  const int64_t G = (group > 0 && group < K) ? group : K;
+  B200Q_REQUIRE(K % G == 0, "awq_search: in_features not divisible by group size");
+  B200Q_REQUIRE(n_cand >= 1 && n_cand <= 32, "awq_search: 1..32 candidates per call");
   B200Q_REQUIRE(aligned16(W) && aligned16(D), "awq_search: unaligned pointer");
   CandParam cp;
   cp.n = n_cand;
@@ -540,14 +582,22 @@ int launch_awq_delta(const void* W, void* D, const uint8_t* salient, int64_t N, 
     cp.sf[i] = i < n_cand ? sf_host[i] : 1.f;
     cp.sf_rcp[i] = 1.0f / cp.sf[i];
   }
-  const int64_t n_groups = N * (K / 128);
-  const int64_t warps_needed = (n_groups + 3) / 4;
-  int64_t blocks = std::min<int64_t>((warps_needed + 7) / 8, (int64_t)kNumSMs * 8);
   const float maxint = (float)((1 << n_bit) - 1);
-  B200Q_DISPATCH_DTYPE(dtype, T,
-                       (awq_delta128_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(
-                           static_cast<const T*>(W), static_cast<__nv_bfloat16*>(D), salient,
-                           n_groups, K, cand_stride, maxint, cp)));
+  const int64_t n_groups = N * (K / G);
+  if (G == 128) {
+    const int64_t warps_needed = (n_groups + 3) / 4;
+    int64_t blocks = std::min<int64_t>((warps_needed + 7) / 8, (int64_t)kNumSMs * 8);
+    B200Q_DISPATCH_DTYPE(dtype, T,
+                         (awq_delta128_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(
+                             static_cast<const T*>(W), static_cast<__nv_bfloat16*>(D), salient,
+                             n_groups, K, cand_stride, maxint, cp)));
+  } else {
+    int64_t blocks = std::min<int64_t>((n_groups + 7) / 8, (int64_t)kNumSMs * 16);
+    B200Q_DISPATCH_DTYPE(dtype, T,
+                         (awq_delta_generic_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(
+                             static_cast<const T*>(W), static_cast<__nv_bfloat16*>(D), salient,
+                             n_groups, G, K, cand_stride, maxint, cp)));
+  }
   count_launch();
   return check_launch("awq_delta");
 }

@@ -555,34 +555,20 @@ __device__ __forceinline__ void asym_params(float mx, float mn, float maxint, fl
   zp = clampf(-rintf(__fdiv_rn(mn, scale)), 0.f, maxint);
 }
 
-// per-row (min,max) over columns [c0, c0+G) -> scale/zero   (groups wider than one block)
-__global__ void __launch_bounds__(256)
-row_range_params_kernel(const float* __restrict__ W, int64_t N, int64_t K, int64_t c0, int64_t G,
-                        float maxint, float* __restrict__ scales, float* __restrict__ zeros) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t c1 = min(K, c0 + G);
-  for (int64_t r = warp; r < N; r += nwarps) {
-    float mx = -INFINITY, mn = INFINITY;
-    for (int64_t c = c0 + lane; c < c1; c += 32) {
-      const float v = W[r * K + c];
-      mx = fmaxf(mx, v); mn = fminf(mn, v);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    }
-    if (lane == 0) asym_params(mx, mn, maxint, scales[r], zeros[r]);
-  }
-}
-
-template <bool OWN_GROUP>
+// GROUP_MODE 0: the quantisation group IS the 128-column block (q_group_size = 128): scale and
+// zero point come from the block's own registers.
+// GROUP_MODE 1: any group size G (K % G == 0, or one group per row).  A group starts wherever the
+// global column index is a multiple of G; its (min, max) is taken over the group's columns AS THEY
+// ARE at that moment (Alg. 1 / the oracle: `if j % G == 0: blk = W[:, j:j+G]`): columns inside the
+// current block come from the registers (they carry the in-block updates), columns beyond the
+// block from global memory (they carry the lazy updates of all earlier blocks and nothing of this
+// one, exactly as in the lazily-updated algorithm).  A group that began in an earlier block hands
+// its parameters over through the per-row scales / zeros arrays.
+template <int GROUP_MODE>
 __global__ void __launch_bounds__(256)
 gptq_block_kernel(float* __restrict__ W, float* __restrict__ Q, float* __restrict__ Err,
                   const float* __restrict__ U, int64_t N, int64_t K, int64_t c0, int nb,
-                  float maxint, const float* __restrict__ scales, const float* __restrict__ zeros) {
+                  float maxint, int64_t G, float* __restrict__ scales, float* __restrict__ zeros) {
   extern __shared__ float Ub[];            // [B][B+1] block of U; row j holds U[c0+j, c0+...]
   constexpr int LD = gc::B + 1;
   for (int i = threadIdx.x; i < gc::B * gc::B; i += blockDim.x) {
@@ -601,8 +587,8 @@ gptq_block_kernel(float* __restrict__ W, float* __restrict__ Q, float* __restric
       w[i] = (c < nb) ? W[r * K + c0 + c] : 0.f;
       qv[i] = 0.f; ev[i] = 0.f;
     }
-    float scale, zp;
-    if constexpr (OWN_GROUP) {
+    float scale = 1.f, zp = 0.f;
+    if constexpr (GROUP_MODE == 0) {
       float mx = -INFINITY, mn = INFINITY;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -614,14 +600,36 @@ gptq_block_kernel(float* __restrict__ W, float* __restrict__ Q, float* __restric
       }
       asym_params(mx, mn, maxint, scale, zp);
     } else {
-      scale = scales[r]; zp = zeros[r];
+      if (c0 % G != 0) { scale = scales[r]; zp = zeros[r]; }   // the group began in an earlier block
     }
-    const Divisor sd(scale);
+    Divisor sd(scale);
 #pragma unroll
     for (int slot = 0; slot < 4; ++slot) {
       for (int o = 0; o < 32; ++o) {
         const int j = slot * 32 + o;
         if (j >= nb) break;
+        if constexpr (GROUP_MODE == 1) {
+          if ((c0 + j) % G == 0) {
+            const int64_t g_end = min(K, c0 + j + G);          // global column range [c0 + j, g_end)
+            float mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = lane + 32 * i;
+              if (c >= j && c < nb && c0 + c < g_end) { mx = fmaxf(mx, w[i]); mn = fminf(mn, w[i]); }
+            }
+            for (int64_t c = c0 + nb + lane; c < g_end; c += 32) {
+              const float v = W[r * K + c];
+              mx = fmaxf(mx, v); mn = fminf(mn, v);
+            }
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+              mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+              mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, s));
+            }
+            asym_params(mx, mn, maxint, scale, zp);
+            sd = Divisor(scale);
+          }
+        }
         const float wj = __shfl_sync(0xffffffffu, w[slot], o);
         const float code = clampf(rintf(sd.div(wj)) + zp, 0.f, maxint);
         const float q = (code - zp) * scale;
@@ -634,6 +642,9 @@ gptq_block_kernel(float* __restrict__ W, float* __restrict__ Q, float* __restric
           if (c > j) w[i] = fmaf(-e, urow[c], w[i]);
         }
       }
+    }
+    if constexpr (GROUP_MODE == 1) {
+      if (lane == 0) { scales[r] = scale; zeros[r] = zp; }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -710,17 +721,17 @@ int64_t b200q_gptq_compensated_workspace(int64_t N, int64_t K) {
 }
 
 // W (fp32 [N,K], destroyed) -> Q (fp32 [N,K]) with U = upper Cholesky factor of H^-1.
-// group: 128 (== block), a larger multiple of 128, or <= 0 (one group per row).
+// group: any size dividing K, or <= 0 (one group per row); 128 takes the register-only fast path.
+// blocksize: the lazy-update batch of Alg. 1.  It only regroups the SAME rank-1 updates (the
+// result is mathematically independent of it), so any positive value is accepted and the kernel
+// batches by its native 128 columns.
 int b200q_gptq_compensated(float* W, float* Q, const float* U, int64_t N, int64_t K, int64_t group,
                            int n_bit, int blocksize, void* work, void* stream) {
   B200Q_REQUIRE(W && Q && U && work && N > 0 && K > 0, "gptq_compensated: bad argument");
   B200Q_REQUIRE(n_bit >= 1 && n_bit <= 16, "gptq_compensated: n_bit must be in [1,16]");
-  if (blocksize != gc::B)
-    return fail(B200Q_EUNSUPPORTED, "gptq_compensated: blocksize must be 128");
-  const int64_t G = group > 0 ? group : K;
-  if (!(G == gc::B || G % gc::B == 0 || G >= K))
-    return fail(B200Q_EUNSUPPORTED, "gptq_compensated: group must be 128, a multiple of 128 or per-row");
-  B200Q_REQUIRE(K % G == 0 || G >= K, "gptq_compensated: in_features not divisible by group size");
+  B200Q_REQUIRE(blocksize >= 1, "gptq_compensated: blocksize must be positive");
+  const int64_t G = (group > 0 && group < K) ? group : K;
+  B200Q_REQUIRE(K % G == 0, "gptq_compensated: in_features not divisible by group size");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   KernelScope scope("gptq_compensated", 2.0 * N * K * 4, (double)N * K * K, st);
   B200Q_REQUIRE(N < (1 << 30) && K < (1 << 30), "gptq_compensated: dimension too large");
@@ -733,8 +744,8 @@ int b200q_gptq_compensated(float* W, float* Q, const float* U, int64_t N, int64_
   uint8_t* planes_u = planes_err + align(split_operand_bytes((int)N, gc::B));
   const float maxint = (float)((1 << n_bit) - 1);
   const int smem = gc::B * (gc::B + 1) * (int)sizeof(float);
-  cudaFuncSetAttribute(gptq_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(gptq_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(gptq_block_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(gptq_block_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int blocks = (int)std::min<int64_t>((N + 7) / 8, (int64_t)kNumSMs * 2);
   // U^T as tensor-core planes, once: the lazy update of block c0 multiplies by U[c0:c1, c1:], whose
   // transpose is the sub-block [c1:, c0:c1] of these planes
@@ -744,15 +755,11 @@ int b200q_gptq_compensated(float* W, float* Q, const float* U, int64_t N, int64_
   for (int64_t c0 = 0; c0 < K; c0 += gc::B) {
     const int nb = (int)std::min<int64_t>(gc::B, K - c0);
     if (G == gc::B) {
-      gptq_block_kernel<true><<<blocks, 256, smem, st>>>(W, Q, Err, U, N, K, c0, nb, maxint, nullptr,
-                                                         nullptr);
+      gptq_block_kernel<0><<<blocks, 256, smem, st>>>(W, Q, Err, U, N, K, c0, nb, maxint, G, nullptr,
+                                                      nullptr);
     } else {
-      if (c0 % G == 0) {
-        row_range_params_kernel<<<blocks, 256, 0, st>>>(W, N, K, c0, G, maxint, scales, zeros);
-        count_launch();
-      }
-      gptq_block_kernel<false><<<blocks, 256, smem, st>>>(W, Q, Err, U, N, K, c0, nb, maxint, scales,
-                                                          zeros);
+      gptq_block_kernel<1><<<blocks, 256, smem, st>>>(W, Q, Err, U, N, K, c0, nb, maxint, G, scales,
+                                                      zeros);
     }
     count_launch();
     const int64_t rest = K - (c0 + nb);

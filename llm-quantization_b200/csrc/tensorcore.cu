@@ -965,8 +965,8 @@ int b200q_awq_search_loss(const void* W, int64_t N, int64_t K, int64_t group, in
                           int dtype, void* work, float* loss, void* stream) {
   B200Q_REQUIRE(W && salient && sf_host && H && work && loss, "awq_search_loss: null pointer");
   B200Q_REQUIRE(N > 0 && K > 0, "awq_search_loss: bad shape");
-  if (group != 128) return fail(B200Q_EUNSUPPORTED, "awq_search_loss: group size must be 128");
-  B200Q_REQUIRE(K % 128 == 0, "awq_search_loss: in_features must be a multiple of 128");
+  // the bf16 operands are read by TMA: 16-byte row pitch
+  B200Q_REQUIRE(K % 8 == 0, "awq_search_loss: in_features must be a multiple of 8");
   B200Q_REQUIRE(aligned16(work), "awq_search_loss: unaligned workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   AwqWork w = awq_layout(work, N, K, n_cand);
@@ -977,7 +977,7 @@ int b200q_awq_search_loss(const void* W, int64_t N, int64_t K, int64_t group, in
                       (double)N * K * (elem_size(dtype) + 2.0 * n_cand), 0, st);
     if (w.rows_pad != N)   // padding rows must be zero: they are read by the GEMM
       cudaMemsetAsync(w.D, 0, 2 * Mtot * K, st);
-    rc = launch_awq_delta(W, w.D, salient, N, K, w.rows_pad * K, n_bit, sf_host, n_cand, dtype, st);
+    rc = launch_awq_delta(W, w.D, salient, N, K, group, w.rows_pad * K, n_bit, sf_host, n_cand, dtype, st);
     if (rc != B200Q_OK) return rc;
   }
   {

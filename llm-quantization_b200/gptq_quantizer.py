@@ -36,7 +36,46 @@ from b200q import pipeline as _pipeline  # noqa: E402
 MODE = "parity"
 BUILD_HESSIAN = True
 GROUP_FACTOR = 4    # under row sharding, layers prepared together = GROUP_FACTOR * world size
+FACTOR_STREAMS = 8  # one GPU: Hessian inverses in flight at a time (each on its own CUDA stream)
 TIMINGS = None      # set to a list to collect (phase, ms) CUDA-event pairs from the model walker
+
+
+class _Prepared:
+    """What the column stage of one layer needs, plus the bookkeeping of an inverse that may still
+    be running on a side stream: `done` (event on that stream), `info_host` (pinned copy of the
+    factorisation's status flag, valid once `done` has completed)."""
+    __slots__ = ("name", "H", "perm", "factor", "done", "info", "info_host", "K")
+
+    def __init__(self, name, H, perm, factor, K, done=None, info=None, info_host=None):
+        self.name, self.H, self.perm, self.factor, self.K = name, H, perm, factor, K
+        self.done, self.info, self.info_host = done, info, info_host
+
+    def check(self):
+        """Wait for the factorisation (host side) and act on its status flag."""
+        if self.done is not None:
+            self.done.synchronize()
+            self.done = None
+        if self.info_host is not None:
+            _report_pivot(int(self.info_host.item()), self.K, self.name)
+            self.info_host = None
+        elif self.info is not None:
+            _report_pivot(int(self.info.item()), self.K, self.name)
+        self.info = None
+
+
+def _report_pivot(j: int, K: int, name: str) -> None:
+    """A non-positive Cholesky pivot means H + 1e-6 I was not positive definite.  The reference
+    hides that behind `except: pinv` (gptq_quantizer.py:161-165) and its output never reads H^-1;
+    parity mode therefore warns and carries on, compensated mode (which multiplies the factor into
+    the weights) raises."""
+    if j == 0:
+        return
+    from b200q import tensor_ops as _tops
+    if MODE == "compensated":
+        _tops.raise_if_not_spd(j, K, f"gptq layer {name!r}")
+    import warnings
+    warnings.warn(f"gptq layer {name!r}: damped Hessian not positive definite (pivot {j}); H^-1 is "
+                  f"not used by the reference-parity output, continuing")
 
 
 # ==================================================================================================
@@ -61,43 +100,124 @@ def gptq_quantize_model_weight(
     items = [(n, m) for n, m in model.named_modules() if isinstance(m, nn.Linear)]
     calibrated = [(n, m) for n, m in items if n in input_feat]
     position = {n: i for i, (n, _) in enumerate(calibrated)}
-    ready = {}
+    ready: Dict[str, _Prepared] = {}
+    retiring: List[_Prepared] = []          # previous group: inverses possibly still in flight
+    side_streams: List[torch.cuda.Stream] = []
+
+    def retire():
+        for p in retiring:
+            p.check()
+        retiring.clear()
+
+    def prepare_sharded(group, device):
+        # Under row sharding the inverse of one layer's Hessian is a single-GPU job, so a GROUP
+        # of layers is prepared at once: every rank adds its calibration samples to each
+        # layer's Hessian (all-reduced), then the ranks factor DIFFERENT layers of the group at
+        # the same time (dealt longest-first by K^3, so a rank that draws an 11008-wide layer
+        # gets fewer 4096-wide ones), and the factors are broadcast.
+        world = _dist.world_size()
+        owner = _deal_layers([(n, m.weight.shape[1]) for n, m in group], world)
+        # three phases, so that no collective sits between two ranks' factorisations (an
+        # all-reduce there would make everybody wait for whoever is busy inverting)
+        t0 = _mark()
+        hessians = [_hessian_stage(input_feat[n], m.weight.shape[1], device, perp_damp, nsamples)
+                    for n, m in group]
+        t1 = _mark()
+        prepared = [_factor_stage(n, H, actorder, owner[n]) for (n, _m), H in zip(group, hessians)]
+        t2 = _mark()
+        flags = []
+        for p in prepared:
+            if p.factor is not None:
+                _dist.broadcast(p.factor, owner[p.name])
+                flags.append(p.info)
+        if flags:
+            # one status exchange and one host sync for the whole group: every rank sees every
+            # owner's flag, so all ranks warn / raise together
+            status = _dist.allreduce_max(torch.cat(flags))
+            for p, j in zip([p for p in prepared if p.factor is not None], status.tolist()):
+                p.info = None
+                _report_pivot(int(j), p.K, p.name)
+        for p in prepared:
+            ready[p.name] = p
+        _lap("hessians", t0, t1)
+        _lap("factors", t1, t2)
+        _lap("broadcast", t2, _mark())
+
+    def prepare_local(group, device):
+        # One GPU: a factorisation is a chain of ~500 small dependent kernels that keeps a few SMs
+        # busy (linalg.cu), so the inverses of a group of layers run CONCURRENTLY, each on its own
+        # stream, while the main stream goes on with the column stages of this group and the
+        # Hessian GEMMs of the next one.  Order of events for group g:
+        #   main : H(g)[0..n)  -> [wait: inverses of g-1 done, flags checked]  -> columns(g) ...
+        #   side k:            wait H(g)[k] -> inverse -> flag to pinned host memory -> done[k]
+        main = torch.cuda.current_stream(device)
+        t0 = _mark()
+        hessians, built = [], []
+        for n, m in group:
+            hessians.append(_hessian_stage(input_feat[n], m.weight.shape[1], device, perp_damp, nsamples))
+            built.append(torch.cuda.Event())
+            built[-1].record(main)
+        t1 = _mark()
+        retire()                      # the previous group's inverses ran under this group's Hessians
+        while len(side_streams) < min(FACTOR_STREAMS, len(group)):
+            side_streams.append(torch.cuda.Stream(device))
+        for k, ((n, m), H) in enumerate(zip(group, hessians)):
+            if H is None:
+                ready[n] = _Prepared(n, None, None, None, m.weight.shape[1])
+                continue
+            side = side_streams[k % len(side_streams)]
+            side.wait_event(built[k])
+            with torch.cuda.stream(side):
+                p = _factor_stage(n, H, actorder, 0)
+                p.info_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+                p.info_host.copy_(p.info, non_blocking=True)
+                p.done = torch.cuda.Event()
+                p.done.record(side)
+            # memory handed across streams: H is read by the side stream, the factor (allocated
+            # there) by the main stream
+            H.record_stream(side)
+            for t in (p.factor, p.perm):
+                if t is not None:
+                    t.record_stream(main)
+            ready[n] = p
+        _lap("hessians", t0, t1)
+        _lap("factors(launch)", t1, _mark())
 
     def compute(name, _module, W):
         if name not in input_feat:
             return _ops.group_fakequant(W, w_bit, q_group_size, symmetric=True)
         if name not in ready:
-            # Under row sharding the inverse of one layer's Hessian is a single-GPU job, so a GROUP
-            # of layers is prepared at once: every rank adds its calibration samples to each
-            # layer's Hessian (all-reduced), then the ranks factor DIFFERENT layers of the group at
-            # the same time (dealt longest-first by K^3, so a rank that draws an 11008-wide layer
-            # gets fewer 4096-wide ones), and the factors are broadcast.  Unsharded: groups of one.
             i = position[name]
             world = _dist.world_size()
-            group = calibrated[i:i + (GROUP_FACTOR * world if world > 1 else 1)]
-            owner = _deal_layers([(n, m.weight.shape[1]) for n, m in group], world)
-            # three phases, so that no collective sits between two ranks' factorisations (an
-            # all-reduce there would make everybody wait for whoever is busy inverting)
-            t0 = _mark()
-            hessians = [_hessian_stage(input_feat[n], m.weight.shape[1], W.device, perp_damp, nsamples)
-                        for n, m in group]
-            t1 = _mark()
-            prepared = [_factor_stage(H, actorder, owner[n]) for (n, _m), H in zip(group, hessians)]
-            t2 = _mark()
-            for (n, _m), p in zip(group, prepared):
-                if p[2] is not None:
-                    _dist.broadcast(p[2], owner[n])
-                ready[n] = p
-            _lap("hessians", t0, t1)
-            _lap("factors", t1, t2)
-            _lap("broadcast", t2, _mark())
-        H, perm, factor = ready.pop(name)
+            if world > 1:
+                prepare_sharded(calibrated[i:i + GROUP_FACTOR * world], W.device)
+            else:
+                prepare_local(calibrated[i:i + max(1, FACTOR_STREAMS)], W.device)
+        p = ready.pop(name)
+        if p.done is not None:
+            if MODE == "compensated":
+                # the column stage multiplies by the factor: it must be finished and sound
+                torch.cuda.current_stream(W.device).wait_event(p.done)
+                p.check()
+            else:
+                retiring.append(p)    # parity output does not read H^-1: join at the group boundary
         t2 = _mark()
-        out = _column_stage(W, w_bit, q_group_size, blocksize, H, perm, factor)
+        out = _column_stage(W, w_bit, q_group_size, blocksize, p.H, p.perm, p.factor)
         _lap("columns", t2, _mark())
         return out
 
-    _pipeline.run_layers(items, compute)
+    try:
+        _pipeline.run_layers(items, compute)
+    finally:
+        for p in list(ready.values()):
+            retiring.append(p)
+        ready.clear()
+        if retiring:
+            main = torch.cuda.current_stream()
+            for p in retiring:
+                if p.done is not None:
+                    main.wait_event(p.done)
+            retire()
 
 
 def _deal_layers(layers, world: int) -> Dict[str, int]:
@@ -184,28 +304,36 @@ def _hessian_stage(input_feat, K: int, device, perp_damp: float, nsamples: int):
     return gptq_hessian(input_feat, K, device, perp_damp, nsamples)
 
 
-def _factor_stage(H, actorder: bool, owner: int = 0):
-    """(H, perm, factor): the act-order permutation (compensated mode only) and what the column
-    stage needs from the inverse -- H^-1 in parity mode (built like the reference builds it; its
-    output does not depend on it), U = chol(H^-1) in compensated mode.  Under row sharding only
-    rank `owner` computes the factor and the caller broadcasts it; no collective happens here."""
+def _factor_stage(name: str, H, actorder: bool, owner: int = 0) -> _Prepared:
+    """The act-order permutation (compensated mode only) and what the column stage needs from the
+    inverse -- H^-1 in parity mode (built like the reference builds it; its output does not depend
+    on it), U = chol(H^-1) in compensated mode -- launched on the CURRENT stream, status flag left
+    on the device (the caller checks it: _Prepared.check).  Under row sharding only rank `owner`
+    computes the factor and the caller broadcasts it; no collective happens here."""
     from b200q import tensor_ops as _tops
     if H is None:
-        return None, None, None
+        return _Prepared(name, None, None, None, 0)
+    K = H.shape[0]
     if MODE == "compensated":
         perm = torch.argsort(torch.diag(H), descending=True) if actorder else None
-        return H, perm, _tops.compensation_factor(H, perm, owner=owner, broadcast=False)
-    return H, None, _tops.spd_inverse(H, ridge=1e-6, owner=owner, broadcast=False)
+        U, info = _tops.compensation_factor(H, perm, owner=owner, broadcast=False, check=False,
+                                            return_info=True)
+        return _Prepared(name, H, perm, U, K, info=info)
+    Hinv, info = _tops.spd_inverse(H, ridge=1e-6, owner=owner, broadcast=False, check=False,
+                                   return_info=True)
+    return _Prepared(name, H, None, Hinv, K, info=info)
 
 
 def _gptq_device(W: torch.Tensor, n_bit: int, q_group_size: int, input_feat, perp_damp: float,
                  blocksize: int, nsamples: int, actorder: bool) -> torch.Tensor:
     """The per-layer stages on a CUDA-resident [N,K] weight; returns the quantized weight."""
     H = _hessian_stage(input_feat, W.shape[1], W.device, perp_damp, nsamples)
-    H, perm, factor = _factor_stage(H, actorder)
-    if factor is not None:
-        _dist.broadcast(factor, 0)
-    return _column_stage(W, n_bit, q_group_size, blocksize, H, perm, factor)
+    p = _factor_stage("layer", H, actorder)
+    if p.factor is not None:
+        _dist.broadcast(p.factor, 0)
+        _dist.broadcast(p.info, 0)
+        p.check()
+    return _column_stage(W, n_bit, q_group_size, blocksize, p.H, p.perm, p.factor)
 
 
 def _column_stage(W: torch.Tensor, n_bit: int, q_group_size: int, blocksize: int, H, perm,

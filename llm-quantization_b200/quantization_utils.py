@@ -131,12 +131,13 @@ _ref_module = None
 def _reference_utils():
     global _ref_module
     if _ref_module is None:
-        root = Path(os.environ.get("LLMQ_REFERENCE_DIR", "/root/reference"))
-        path = root / "quantization_utils.py"
-        if not path.exists():
+        from b200q.build import reference_dir
+        root = reference_dir()
+        if root is None:
             raise ImportError(
                 f"{', '.join(_PASSTHROUGH)} are not part of the B200 hot path and are taken from a "
-                f"reference checkout; none found at {root} (set LLMQ_REFERENCE_DIR)")
+                f"reference checkout; none found (set LLMQ_REFERENCE_DIR)")
+        path = root / "quantization_utils.py"
         spec = importlib.util.spec_from_file_location("_llmq_reference_quantization_utils", path)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)

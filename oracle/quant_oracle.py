@@ -323,20 +323,27 @@ def awq_search_losses(W: torch.Tensor, H: torch.Tensor, salient: torch.Tensor, n
 
 @torch.no_grad()
 def gptq_compensated(W: torch.Tensor, H: torch.Tensor, n_bit: int, group: int,
-                     blocksize: int = 128, perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     blocksize: int = 128, perm: Optional[torch.Tensor] = None,
+                     return_margin: bool = False):
     """GPTQ (Frantar et al. 2022, Alg. 1) with the asymmetric per-group grid of
     pseudo_quantize_tensor: the loop gptq_quantizer.py:173-197 sketches and then skips.
-    H must already include the damping.  float64 reference arithmetic."""
+    H must already include the damping.  float64 reference arithmetic.
+    return_margin: also return, per element, the distance of the (compensated) value from the
+    nearest rounding boundary in code units, 0 = exactly on a tie -- lets a test tell a legitimate
+    tie flip of an fp32 implementation from an error."""
     Wd = W.double().clone()
     N, K = Wd.shape
     G = group if group > 0 else K
     if perm is not None:
         inv = torch.argsort(perm)
-        return gptq_compensated(W[:, perm], H[perm][:, perm], n_bit, group, blocksize)[:, inv]
+        res = gptq_compensated(W[:, perm], H[perm][:, perm], n_bit, group, blocksize,
+                               return_margin=return_margin)
+        return (res[0][:, inv], res[1][:, inv]) if return_margin else res[:, inv]
     Hinv = torch.linalg.inv(H.double())
     U = torch.linalg.cholesky(Hinv, upper=True)
     qmax = 2 ** n_bit - 1
     Q = torch.zeros_like(Wd)
+    margin = torch.zeros_like(Wd)
     scale = zero = None
     for c0 in range(0, K, blocksize):
         c1 = min(c0 + blocksize, K)
@@ -348,13 +355,15 @@ def gptq_compensated(W: torch.Tensor, H: torch.Tensor, n_bit: int, group: int,
                 scale = (hi - lo).clamp(min=1e-5) / qmax
                 zero = (-torch.round(lo / scale)).clamp(0, qmax)
             col = Wd[:, j]
-            qc = (torch.clamp(torch.round(col / scale) + zero, 0, qmax) - zero) * scale
+            x = col / scale
+            margin[:, j] = (x - torch.floor(x) - 0.5).abs()
+            qc = (torch.clamp(torch.round(x) + zero, 0, qmax) - zero) * scale
             Q[:, j] = qc
             e = (col - qc) / U[j, j]
             Wd[:, j + 1:c1] -= e.unsqueeze(1) * U[j, j + 1:c1].unsqueeze(0)
             Err[:, j - c0] = e
         Wd[:, c1:] -= Err @ U[c0:c1, c1:]
-    return Q.to(W.dtype)
+    return (Q.to(W.dtype), margin) if return_margin else Q.to(W.dtype)
 
 
 # --------------------------------------------------------------------------------------------------
