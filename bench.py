@@ -2,30 +2,39 @@
 """bench.py — quantize-only throughput of the weight-quantization hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                    [--method awq|awq_fixed|gptq|gptq_fast|pot|apot|smoothquant]
-                    [--model llama2-7b|llama3-8b|opt-125m|tiny] [--dtype f32|f16|bf16]
+                    [--method default|awq|awq_fixed|gptq|gptq_fast|pot|apot|smoothquant|smoothquant_search]
+                    [--model llama2-7b|llama3-8b|opt-125m|tiny|matrix-NxK] [--dtype f32|f16|bf16]
 
 One "step" = one pass of the chosen method over EVERY nn.Linear of the named model shape
 (random-init weights, synthetic calibration activations), driven through the reference-compatible
 entry points of llm-quantization_b200/ (`awq_search_scale_factor`, `awq_quantize_model_weight`,
 `gptq_quantize_model_weight`, ...).
 
-Default workload = BASELINE.json configs[1]: Llama-2-7B shapes, AWQ w4 g128 WITH the 20-point scale
-grid search.  Per Linear that is: per-batch mean|x| statistics of the 128 x 2048-token calibration
-activations, the Gram matrix X^T X (tcgen05 GEMM), the 20 candidate reconstruction losses
-tr(dW H dW^T) (tcgen05 GEMM), and the fused scale/quantize/unscale pass with the winning factor.
+Default (`--method default`) = BASELINE.json's metric "Llama-7B GPTQ/AWQ w4g128 quantize seconds":
+the top-level line is configs[1] -- Llama-2-7B shapes, AWQ w4 g128 WITH the 20-point scale grid
+search (per Linear: per-batch mean|x| statistics of the 128 x 2048-token calibration activations,
+the Gram matrix X^T X (tcgen05 GEMM), the 20 candidate reconstruction losses tr(dW H dW^T)
+(tcgen05 GEMM), the fused scale/quantize/unscale pass with the winning factor) -- and the sibling
+block `"gptq"` is the same model through `gptq_quantize_model_weight` (Hessian + damped inverse +
+column stage), timed in the same process in its own region, with its own `roofline`, `e2e`,
+`cpu_baseline` and `stages`.
 At N > 1 every Linear's output rows are sharded over the ranks and the calibration samples are
-dealt to them (Gram partials all-reduced over NCCL, candidate losses all-reduced): strong scaling.
+dealt to them (Gram / Hessian partials all-reduced over NCCL, H^-1 broadcast, candidate losses
+all-reduced): strong scaling.
 
 JSON line: `value` = rows/s with weights and activations resident in HBM; `seconds` = s per model;
 `e2e` = the same entry points on a model whose weights sit in pinned HOST memory (H2D / D2H of every
 weight inside the timed region; activations stay on the device, where the out-of-scope forward pass
-leaves them — gptq_quantizer.py:243-246); `roofline` = the dominant kernel, timed with CUDA events
-inside the timed steps by the library itself; `cpu_baseline` = the oracle port on this box's host
-cores on a bounded sample; `clocks`; `gpu_launches`.
+leaves them -- gptq_quantizer.py:243-246); `roofline` = the dominant kernel, timed with CUDA events
+inside the timed steps by the library itself: `achieved` counts the MMAs the kernel EXECUTES (the
+SYRK runs the tiles that touch the upper triangle), `algorithmic_tflops` the full 2*T*K^2 of
+SURVEY.md 8(d); `cpu_baseline` = the reference's own functions (imported unmodified from
+baseline/_ref) on this box's host cores on a bounded sample; `clocks`; `gpu_launches`.
 
-`--impl reference` times the CPU oracle port only: the reference is pure Python/torch, its tree
-is absent on the GPU box, and the oracle is pinned bit-for-bit against it by tests/golden.
+`--impl reference` times the reference's CPU implementation only: the unmodified reference modules
+staged in baseline/_ref (by __graft_entry__.build()), driven through their own entry points on
+fixed row / token samples and extrapolated; the oracle port is the fallback when the staged files
+are absent, and the stand-in for the AWQ search, whose body is a stub in the reference.
 """
 from __future__ import annotations
 
@@ -61,13 +70,18 @@ W_BIT, GROUP = 4, 128
 N_CALIB, CALIB_TOKENS = 128, 2048        # calibration batches x tokens per batch
 N_GRID = 20
 DTYPES = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
-METHODS = ("awq", "awq_fixed", "gptq", "gptq_fast", "pot", "apot", "smoothquant", "smoothquant_search")
+METHODS = ("default", "awq", "awq_fixed", "gptq", "gptq_fast", "pot", "apot", "smoothquant",
+           "smoothquant_search")
 NEEDS_ACTS = ("awq", "gptq")
 # dominant C-ABI entry point per method: (name, bound)
 DOMINANT = {"awq": ("hessian_gemm", "tensor"), "gptq": ("hessian_gemm", "tensor"),
             "awq_fixed": ("group_fakequant", "hbm"), "gptq_fast": ("gptq_parity_quant", "hbm"),
             "smoothquant": ("group_fakequant", "hbm"), "pot": ("pot_quant", "hbm"),
             "apot": ("apot_quant", "hbm"), "smoothquant_search": ("smooth_alpha_errors", "hbm")}
+STAGE_NAMES = ("hessian_gemm", "hessian_prescale", "hessian_reduce", "awq_search_gemm", "awq_search_delta",
+               "awq_search_fold", "act_meanabs", "group_fakequant", "gptq_parity_quant", "col_absmax",
+               "spd_inverse", "pot_quant", "apot_quant", "seq_sum_rows", "smooth_alpha_errors",
+               "smooth_scale")
 
 
 def layer_list(model: str):
@@ -150,9 +164,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # one step of each method through the public entry points
 # ------------------------------------------------------------------------------------------------
-def make_step(method: str, acts_by_K, stats_by_K, act_scale_by_K):
+def make_step(method: str, acts_by_K, stats_by_K, act_scale_by_K, host: bool = False):
     import awq_quantizer, gptq_quantizer, pot_apot_quantizer, smooth_quant_quantizer
-    from b200q import ops
+    from b200q import pipeline
 
     def by_layer(model, table):
         return {n: table[m.in_features] for n, m in model.named_modules() if isinstance(m, nn.Linear)}
@@ -160,13 +174,18 @@ def make_step(method: str, acts_by_K, stats_by_K, act_scale_by_K):
     if method == "awq":
         def step(model):
             # (a10) per-batch mean|x| statistics, as the calibration hooks would collect them
-            # (a data-parallel calibration run produces them per rank: batches dealt, rows gathered)
-            stats = {K: awq_quantizer._stat_rows(x, x.device) for K, x in acts_by_K.items()}
-            # (a9) 20-point grid search on the raw activations, (a8) quantize with the winner
-            best = awq_quantizer.awq_search_scale_factor(model, W_BIT, GROUP, by_layer(model, acts_by_K),
-                                                         protect_ratio=0.01, n_grid=N_GRID)
-            awq_quantizer.awq_quantize_model_weight(model, W_BIT, GROUP, by_layer(model, stats),
-                                                    protect_ratio=0.01, scale_factor=best)
+            # (a data-parallel calibration run produces them per rank: batches dealt, rows gathered);
+            # the host-weights run gets them on the host, where the reference's hooks leave them
+            stats = stats_by_K if host else \
+                {K: awq_quantizer._stat_rows(x, x.device) for K, x in acts_by_K.items()}
+            # (a9) 20-point grid search on the raw activations, (a8) quantize with the winner.
+            # Host-resident weights: the device copy made for the search serves the quantize pass
+            # too (pipeline.keep_resident), so every weight crosses PCIe once in each direction.
+            with pipeline.keep_resident():
+                best = awq_quantizer.awq_search_scale_factor(model, W_BIT, GROUP, by_layer(model, acts_by_K),
+                                                             protect_ratio=0.01, n_grid=N_GRID)
+                awq_quantizer.awq_quantize_model_weight(model, W_BIT, GROUP, by_layer(model, stats),
+                                                        protect_ratio=0.01, scale_factor=best)
             return best
         return step
     if method == "awq_fixed":
@@ -190,86 +209,230 @@ def make_step(method: str, acts_by_K, stats_by_K, act_scale_by_K):
         def step(model):
             # (a18) 20-point alpha sweep, (a17) smooth + quantize with the winner
             scales = by_layer(model, act_scale_by_K)
-            alpha = smooth_quant_quantizer.smoothquant_search_alpha(model, [], scales, 8, GROUP,
-                                                                    n_grid=N_GRID, verbose=False)
-            smooth_quant_quantizer.smoothquant_quantize_model_weight(model, 8, GROUP, scales,
-                                                                     alpha=alpha, verbose=False)
+            with pipeline.keep_resident():
+                alpha = smooth_quant_quantizer.smoothquant_search_alpha(model, [], scales, 8, GROUP,
+                                                                        n_grid=N_GRID, verbose=False)
+                smooth_quant_quantizer.smoothquant_quantize_model_weight(model, 8, GROUP, scales,
+                                                                         alpha=alpha, verbose=False)
             return alpha
         return step
     raise SystemExit(f"unknown method {method}")
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port on the host cores, bounded sample per distinct shape, extrapolated
+# CPU baseline: the reference's own functions on the host cores, FIXED samples per distinct shape
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(method: str, model: str, dtype, tokens_total: int, budget_s: float = 25.0):
+CPU_TOKENS = 2048        # calibration tokens fed to the activation-side stages
+
+
+def cpu_rows(method: str, N: int, K: int) -> int:
+    """Weight rows per distinct Linear shape the CPU arm works on.  A fixed function of the shape
+    (NOT of a time budget): both arms and every step use the same slices."""
+    per = {"pot": 1 << 19, "apot": 1 << 20, "smoothquant_search": 1 << 19, "awq": 1 << 21}.get(method, 1 << 23)
+    return min(N, max(64, per // K // 64 * 64))
+_REF_CACHE = {}
+
+
+def _reference_modules():
+    """The UNMODIFIED reference modules from baseline/_ref (staged by __graft_entry__.build()),
+    imported under private names so they cannot shadow the drop-in modules; None when absent."""
+    if "mods" in _REF_CACHE:
+        return _REF_CACHE["mods"]
+    mods = None
+    ref = REPO / "baseline" / "_ref"
+    if (ref / "gptq_quantizer.py").exists():
+        import importlib.util
+        mods = {}
+        saved = {k: sys.modules.get(k) for k in ("quantization_utils",)}
+        try:
+            # the reference's quantizer modules do `from quantization_utils import ...` at import
+            # time: give them THEIR quantization_utils for the duration of the import
+            for name in ("quantization_utils", "gptq_quantizer", "awq_quantizer", "pot_apot_quantizer",
+                         "smooth_quant_quantizer"):
+                spec = importlib.util.spec_from_file_location(f"_llmq_ref_{name}", ref / f"{name}.py")
+                mod = importlib.util.module_from_spec(spec)
+                if name == "quantization_utils":
+                    sys.modules["quantization_utils"] = mod
+                spec.loader.exec_module(mod)
+                mods[name] = mod
+        except Exception as exc:  # missing optional dependency of the reference, ...
+            print(f"[bench] reference import failed ({exc!r}); falling back to the oracle port",
+                  file=sys.stderr)
+            mods = None
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    sys.modules.pop(k, None)
+                else:
+                    sys.modules[k] = v
+    _REF_CACHE["mods"] = mods
+    return mods
+
+
+def _best_of(fn, reps: int = 2):
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def cpu_baseline(method: str, model: str, dtype, tokens_total: int):
+    """Seconds per model of the reference's CPU path, from fixed samples: per distinct Linear shape
+    cpu_rows() weight rows and CPU_TOKENS calibration tokens, scaled by rows / tokens / layer
+    count.  kind = "reference" when the staged reference modules ran.  `sample_seconds` is the wall
+    time this call actually spent (one "step" of the reference arm)."""
     from oracle import quant_oracle as O
+    ref = _reference_modules()          # (first call imports transformers / datasets: not timed)
+    t_call = time.perf_counter()
     torch.set_num_threads(os.cpu_count() or 1)
     g = torch.Generator().manual_seed(1234)
-    shapes = MODELS[model]
-    per = budget_s / len(shapes)
     total_s, total_rows, notes = 0.0, 0, []
-    for name, N, K, count in shapes:
-        elem_cost = {"pot": 2e-6, "apot": 1.4e-6, "smoothquant_search": 5e-7}.get(
-            method, 2e-8 if method != "awq" else 6e-7)
-        rows = N if elem_cost * N * K <= per else max(64, int(per / (elem_cost * K)) // 64 * 64)
-        rows = min(rows, N)
+    legs = set()
+    for name, N, K, count in MODELS[model]:
+        rows = cpu_rows(method, N, K)
         w = (torch.randn(rows, K, generator=g) * 0.02).to(dtype)
         feats = [torch.rand(K, generator=g) for _ in range(N_CALIB)]
         act = torch.rand(K, generator=g) * 5
-        extra = 0.0
-        t0 = time.perf_counter()
+        lin = nn.Linear(K, rows, bias=False)
+        net = nn.Sequential(lin)
+
+        def fresh():
+            lin.weight.data = w.clone()
+
+        row_scaled = 0.0     # seconds that scale with the number of weight rows
+        fixed = 0.0          # seconds per layer independent of the rows (Hessian, inverse, stats)
         if method in ("awq", "gptq"):
-            # activation-side work on a token sample, scaled to the full calibration set
-            tok = min(tokens_total, 2048)
-            x = torch.randn(tok, K, generator=g)
-            t1 = time.perf_counter()
-            if method == "awq":
-                O.act_meanabs(x)
-                H = (x.T @ x) / tok
-            else:
-                H = O.gptq_hessian([x], K, torch.float32, 128, 0.01)
-                O.gptq_hinv(H)
-            extra = (time.perf_counter() - t1)
-            t_inv = 0.0
-            if method == "gptq":
-                t2 = time.perf_counter(); O.gptq_hinv(H); t_inv = time.perf_counter() - t2
-            # the X-dependent part scales with tokens, the inverse does not
-            extra = (extra - t_inv) * (tokens_total / tok) + t_inv
+            tok = min(tokens_total, CPU_TOKENS)
+            x = torch.randn(tok, K, generator=g).to(dtype)
+        if method == "awq":
+            # (a10) the hook's reduction, quantization_utils.py:231, per calibration batch
+            t_stat = _best_of(lambda: x.view(-1, K).abs().mean(dim=0))
+            fixed += t_stat * (tokens_total / tok)
+            # (a9) search: the reference's body is a stub -- time the builder's restatement of its
+            # docstring (fp32 Gram matrix on the sample + per-candidate quantize and tr(dW H dW^T))
             t0 = time.perf_counter()
-            if method == "awq":
-                imp = sum(feats)
-                sal = torch.topk(imp, max(1, int(K * 0.01)))[1]
-                cands = torch.linspace(1, 2, N_GRID, dtype=torch.float64).tolist()
-                losses = O.awq_search_losses(w.float(), H, sal, W_BIT, GROUP, cands)
-                O.awq_layer(w, feats, W_BIT, GROUP, 0.01, cands[int(torch.argmin(losses))])
+            H = (x.float().T @ x.float()) / tok
+            fixed += (time.perf_counter() - t0) * (tokens_total / tok)
+            imp = sum(feats)
+            sal = torch.topk(imp, max(1, int(K * 0.01)))[1]
+            cands = torch.linspace(1, 2, N_GRID, dtype=torch.float64).tolist()
+            t0 = time.perf_counter()
+            losses = O.awq_search_losses(w.float(), H, sal, W_BIT, GROUP, cands)
+            row_scaled += time.perf_counter() - t0
+            legs.add("search: builder restatement (reference is a stub)")
+            best = cands[int(torch.argmin(losses))]
+            # (a8) the reference's own walker
+            if ref:
+                def run():
+                    fresh()
+                    ref["awq_quantizer"].awq_quantize_model_weight(net, W_BIT, GROUP, {"0": feats}, 0.01, best)
+                row_scaled += _best_of(run)
+                legs.add("awq_quantize_model_weight: imported reference")
             else:
-                O.gptq_parity_quant(w, W_BIT)
+                row_scaled += _best_of(lambda: O.awq_layer(w, feats, W_BIT, GROUP, 0.01, best))
+        elif method == "gptq":
+            if ref:
+                # the reference's _gptq_quantize_layer on 1 and on 5 calibration samples of `tok`
+                # tokens: the difference is 4x the per-sample Hessian cost (gptq_quantizer.py:137-144),
+                # the rest (inverse :160-165, K-iteration column loop :173-197) is per layer
+                def run(n):
+                    fresh()
+                    ref["gptq_quantizer"]._gptq_quantize_layer(lin, W_BIT, GROUP, [x] * n, actorder=True,
+                                                               verbose=False)
+                t1 = _best_of(lambda: run(1), 1)
+                t5 = _best_of(lambda: run(5), 1)
+                per_sample = max(t5 - t1, 0.0) / 4
+                fixed += per_sample * (tokens_total / tok) + max(t1 - per_sample, 0.0)
+                legs.add("_gptq_quantize_layer: imported reference (its column loop is a Python loop "
+                         "over K columns whose cost barely depends on the rows: counted per layer)")
+            else:
+                t0 = time.perf_counter()
+                H = O.gptq_hessian([x], K, torch.float32, 128, 0.01)
+                fixed += (time.perf_counter() - t0) * (tokens_total / tok)
+                fixed += _best_of(lambda: O.gptq_hinv(H), 1)
+                row_scaled += _best_of(lambda: O.gptq_parity_quant(w, W_BIT))
         elif method == "awq_fixed":
-            O.awq_layer(w, feats, W_BIT, GROUP, 0.01, 2.0)
+            if ref:
+                def run():
+                    fresh()
+                    ref["awq_quantizer"].awq_quantize_model_weight(net, W_BIT, GROUP, {"0": feats}, 0.01, 2.0)
+                row_scaled += _best_of(run)
+            else:
+                row_scaled += _best_of(lambda: O.awq_layer(w, feats, W_BIT, GROUP, 0.01, 2.0))
         elif method == "gptq_fast":
-            O.gptq_parity_quant(w, W_BIT)
+            row_scaled += _best_of(lambda: O.gptq_parity_quant(w, W_BIT))
+            legs.add("closed form of the reference's column loop (oracle port)")
         elif method == "pot":
-            O.pot_quant(w, W_BIT, GROUP)
+            fn = ref["pot_apot_quantizer"].pot_quantize_tensor if ref else \
+                (lambda t, n_bit, q_group_size: O.pot_quant(t, n_bit, q_group_size))
+            row_scaled += _best_of(lambda: fn(w, n_bit=W_BIT, q_group_size=GROUP), 1)
         elif method == "apot":
-            O.apot_quant(w, W_BIT, GROUP, 2, total_elements=N * K)
+            # (the grid follows from the element count of the tensor handed in: the slice is kept
+            # above 500000 elements so the reference picks the same 20-point grid as for the layer)
+            if ref and rows * K > 500000:
+                row_scaled += _best_of(lambda: ref["pot_apot_quantizer"].apot_quantize_tensor(
+                    w, n_bit=W_BIT, q_group_size=GROUP, k=2), 1)
+            else:
+                row_scaled += _best_of(lambda: O.apot_quant(w, W_BIT, GROUP, 2, total_elements=N * K), 1)
         elif method == "smoothquant":
-            O.smoothquant_layer(w, act, 0.5, 8, GROUP)
+            if ref:
+                def run():
+                    fresh()
+                    if hasattr(lin, "smoothing_scale"):
+                        del lin.smoothing_scale
+                    ref["smooth_quant_quantizer"].smoothquant_quantize_model_weight(
+                        net, 8, GROUP, {"0": act}, alpha=0.5, verbose=False)
+                row_scaled += _best_of(run)
+            else:
+                row_scaled += _best_of(lambda: O.smoothquant_layer(w, act, 0.5, 8, GROUP))
         elif method == "smoothquant_search":
             alphas = torch.linspace(0, 1, N_GRID, dtype=torch.float64).tolist()
+            t0 = time.perf_counter()
             S = torch.stack([O.smooth_scale(act.clamp(min=1e-5), w, a).float() for a in alphas])
             errs = O.smooth_alpha_errors(w, S.to(w.dtype).float(), act, 8, GROUP)
             O.smoothquant_layer(w, act, alphas[int(torch.argmin(errs))], 8, GROUP)
-        dt = (time.perf_counter() - t0) * (N / rows) + extra
+            row_scaled += time.perf_counter() - t0
+            legs.add("alpha sweep: builder restatement (reference is a stub)")
+        dt = row_scaled * (N / rows) + fixed
         total_s += dt * count
         total_rows += N * count
         notes.append(f"{rows}x{K}")
+    kind = "reference" if (ref and method in ("awq", "awq_fixed", "gptq", "pot", "apot", "smoothquant")) else "port"
     return {"value": total_rows / total_s, "unit": "rows/s", "seconds_per_model": total_s,
-            "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "oracle port (torch CPU ops, all host threads) timed once per distinct Linear shape "
-                      "on row slices " + ", ".join(notes) +
-                      (f" and a {min(tokens_total, 2048)}-token activation sample" if method in NEEDS_ACTS else "") +
+            "sample_seconds": time.perf_counter() - t_call,
+            "cores": torch.get_num_threads(), "kind": kind,
+            "legs": sorted(legs),
+            "sample": ("unmodified reference functions (baseline/_ref) " if kind == "reference" else
+                       "oracle port (torch CPU ops) ") +
+                      "on all host threads, once per distinct Linear shape on the first rows " +
+                      ", ".join(notes) +
+                      (f" and {min(tokens_total, CPU_TOKENS)} calibration tokens" if method in NEEDS_ACTS else "") +
                       f" of {model}; whole-model time extrapolated by rows, tokens and layer count"}
+
+
+def executed_fraction_syrk(K: int) -> float:
+    """Share of the 128 x 256 output tiles of X^T X that touch the upper triangle (= run)."""
+    tm, tn = -(-K // 128), -(-K // 256)
+    return sum(1 for m in range(tm) for n in range(tn) if (n + 1) * 256 > m * 128) / (tm * tn)
+
+
+def describe(method: str, args, bits: int) -> str:
+    return {"awq": f"AWQ w{bits} g{GROUP} with the {N_GRID}-point scale grid search "
+                   f"(activation stats + Gram matrix + candidate losses + quantize), "
+                   f"{args.calib_batches} x {args.calib_tokens}-token calibration activations (bf16)",
+            "awq_fixed": f"AWQ w{bits} g{GROUP}, fixed scale factor 2.0 (benchmark_runner flow)",
+            "gptq": f"GPTQ w{bits} act-order: Hessian + damped inverse + reference-parity column stage, "
+                    f"{args.calib_batches} x {args.calib_tokens}-token calibration activations (bf16)",
+            "gptq_fast": f"GPTQ w{bits}, reference-parity column stage only (H, H^-1 cannot reach the output)",
+            "pot": f"POT w{bits} g{GROUP}, 200-point scale search",
+            "apot": f"APOT w{bits} g{GROUP} k2, 20-point scale search",
+            "smoothquant": f"SmoothQuant w{bits} g{GROUP} alpha 0.5 (weight side; the reference has no "
+                           f"activation quantizer, smooth_quant_quantizer.py:363-371)",
+            "smoothquant_search": f"SmoothQuant w{bits} g{GROUP} with the {N_GRID}-point alpha sweep "
+                                  f"(weight-side reconstruction error per alpha + smooth + quantize; the "
+                                  f"reference has no activation (A8) quantizer)"}[method]
 
 
 def main():
@@ -277,7 +440,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--method", default="awq", choices=METHODS)
+    ap.add_argument("--method", default="default", choices=METHODS,
+                    help="default = AWQ + search (top-level line) and GPTQ (sibling block 'gptq')")
     ap.add_argument("--model", default="llama2-7b",
                     help="one of " + ", ".join(sorted(MODELS)) + ", or matrix-NxK for a single Linear "
                          "(BASELINE configs[4]: the 4096x4096 ... 28672x8192 sweep)")
@@ -311,39 +475,58 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     dtype = DTYPES[args.dtype]
     tokens_total = args.calib_batches * args.calib_tokens
-    bits = 8 if args.method.startswith("smoothquant") else W_BIT
-    what = {"awq": f"AWQ w{bits} g{GROUP} with the {N_GRID}-point scale grid search "
-                   f"(activation stats + Gram matrix + candidate losses + quantize), "
-                   f"{args.calib_batches} x {args.calib_tokens}-token calibration activations (bf16)",
-            "awq_fixed": f"AWQ w{bits} g{GROUP}, fixed scale factor 2.0 (benchmark_runner flow)",
-            "gptq": f"GPTQ w{bits} act-order: Hessian + damped inverse + reference-parity column stage, "
-                    f"{args.calib_batches} x {args.calib_tokens}-token calibration activations (bf16)",
-            "gptq_fast": f"GPTQ w{bits}, reference-parity column stage only (H, H^-1 cannot reach the output)",
-            "pot": f"POT w{bits} g{GROUP}, 200-point scale search",
-            "apot": f"APOT w{bits} g{GROUP} k2, 20-point scale search",
-            "smoothquant": f"SmoothQuant w{bits} g{GROUP} alpha 0.5",
-            "smoothquant_search": f"SmoothQuant w{bits} g{GROUP} with the {N_GRID}-point alpha sweep "
-                                  f"(reconstruction error per alpha + smooth + quantize)"}[args.method]
-    workload = f"{args.model}-shape {what}; every nn.Linear incl. lm_head, random-init {args.dtype} weights"
+    methods = ["awq", "gptq"] if args.method == "default" else [args.method]
+    primary = methods[0]
     total_rows = sum(N * c for _, N, _, c in MODELS[args.model])
     total_elems = sum(N * K * c for _, N, K, c in MODELS[args.model])
-    metric = f"{args.model}_{args.method}_w{bits}g{GROUP}_quantize_rows_per_s"
+
+    def bits_of(m):
+        return 8 if m.startswith("smoothquant") else W_BIT
+
+    def metric_of(m):
+        return f"{args.model}_{m}_w{bits_of(m)}g{GROUP}_quantize_rows_per_s"
+
+    def workload_of(m):
+        return (f"{args.model}-shape {describe(m, args, bits_of(m))}; every nn.Linear incl. lm_head, "
+                f"random-init {args.dtype} weights")
+
+    def config_of(m):
+        return {"workload": workload_of(m), "linears": len(layer_list(args.model)), "rows": total_rows,
+                "weights": total_elems,
+                "sharding": f"output rows / {world}, calibration samples / {world}",
+                "l2": "inputs larger than L2 (per-step weight and activation bytes >> 126 MB), no flush"}
 
     if args.impl == "reference":
+        # The reference's CPU implementation on this box's host cores.  One STEP = one pass over the
+        # bounded sample (fixed row / token slices of every distinct Linear shape); `ms_per_step`
+        # is the wall time of such a pass, `value` / `seconds` the whole-model figure extrapolated
+        # from the mean over the timed passes.  The sibling method of the default run is sampled
+        # once (its pass includes 11008-wide LAPACK inverses: ~40 s).
         if rank != 0:
             return
-        vals = [cpu_baseline(args.method, args.model, dtype, tokens_total, budget_s=20.0)
-                for _ in range(args.warmup + args.steps)][args.warmup:]
-        best = max(vals, key=lambda r: r["value"])
-        print(json.dumps({
-            "impl": "reference", "metric": metric, "value": best["value"], "unit": "rows/s",
-            "seconds": best["seconds_per_model"], "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": best["seconds_per_model"] * 1e3,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
-            "data": "synthetic", "config": {"workload": workload}, "cpu_baseline": best,
-            "e2e": {"value": best["value"], "unit": "rows/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}), file=out, flush=True)
+        blocks = {}
+        for i, m in enumerate(methods):
+            once = i > 0 or m in ("pot", "apot", "gptq")
+            n_warm, n_steps = (0, 1) if once else (args.warmup, args.steps)
+            vals = [cpu_baseline(m, args.model, dtype, tokens_total) for _ in range(n_warm + n_steps)][n_warm:]
+            secs = sum(v["seconds_per_model"] for v in vals) / len(vals)
+            best = dict(vals[-1])
+            best.update(value=total_rows / secs, seconds_per_model=secs)
+            blocks[m] = {
+                "impl": "reference", "metric": metric_of(m), "value": total_rows / secs, "unit": "rows/s",
+                "seconds": secs,
+                "ms_per_step": sum(v["sample_seconds"] for v in vals) / len(vals) * 1e3,
+                "steps_timed": len(vals),
+                "config": config_of(m), "cpu_baseline": best,
+                "e2e": {"value": total_rows / secs, "unit": "rows/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        line = dict(blocks[primary])
+        line.update({"n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                     "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                     "dtype": args.dtype, "data": "synthetic", "gpu_launches": 0})
+        for m in methods[1:]:
+            line[m] = blocks[m]
+        print(json.dumps(line), file=out, flush=True)
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU path exists)"
@@ -369,7 +552,7 @@ def main():
         originals[key] = w
     Ks = sorted({K for _, _, K in layers})
     acts_by_K = {}
-    if args.method in NEEDS_ACTS:
+    if any(m in NEEDS_ACTS for m in methods):
         acts_by_K = {K: synth_acts(K, device, 7 + K, args.calib_batches, args.calib_tokens) for K in Ks}
         stats_by_K = {K: ops.act_meanabs_batched(x).to(x.dtype) for K, x in acts_by_K.items()}
     else:
@@ -377,8 +560,6 @@ def main():
         stats_by_K = {K: ops.act_meanabs_batched(x).float() for K, x in small.items()}
         del small
     act_scale_by_K = {K: v.float().amax(0) * 4 for K, v in stats_by_K.items()}
-    step_fn = make_step(args.method, acts_by_K, stats_by_K, act_scale_by_K)
-    local_bytes = sum(w.numel() * w.element_size() for w in originals.values())
 
     def reset(m, src):
         for n, lin in m.layers.items():
@@ -389,65 +570,19 @@ def main():
             td.barrier()
         torch.cuda.synchronize()
 
-    def one_step(m=model):
-        if m is model:
-            reset(model, originals)
-        if world > 1:
-            with bdist.row_sharded():
-                return step_fn(m)
-        return step_fn(m)
+    peaks = json.loads((REPO / "MEASURED_PEAKS.json").read_text()) if (REPO / "MEASURED_PEAKS.json").exists() else {}
+    src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
 
-    for _ in range(args.warmup):
-        one_step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = _lib.launch_count()
-    _lib.profile_enable(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    walker_timings = None
-    if os.environ.get("B200Q_WALKER_TIMINGS") and args.method == "gptq":
-        import gptq_quantizer as _gq
-        walker_timings = _gq.TIMINGS = []
-    barrier()
-    e0.record()
-    result = None
-    for _ in range(args.steps):
-        result = one_step()
-    e1.record()
-    barrier()
-    if walker_timings is not None:
-        torch.cuda.synchronize()
-        phases = {}
-        for ph, a, b in walker_timings:
-            phases[ph] = phases.get(ph, 0.0) + a.elapsed_time(b) / args.steps
-        print(f"[rank {rank}] walker phases (ms/step): " +
-              ", ".join(f"{k} {v:.1f}" for k, v in phases.items()), file=sys.stderr, flush=True)
-        _gq.TIMINGS = None
-    _lib.profile_enable(False)
-    ms_total = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    dom_name, dom_bound = DOMINANT[args.method]
-    kq = {n: _lib.profile_query(n) for n in
-          ("hessian_gemm", "hessian_prescale", "hessian_reduce", "awq_search_gemm", "awq_search_delta", "awq_search_fold",
-           "act_meanabs", "group_fakequant", "gptq_parity_quant", "col_absmax", "spd_inverse",
-           "pot_quant", "apot_quant", "seq_sum_rows", "smooth_alpha_errors", "smooth_scale")}
-    kall = _lib.profile_query(None)
+    # the host-resident copy of the model (pinned), shared by the e2e runs of all methods
+    host_pack = {}
 
-    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
-    if world > 1:
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-
-    # ---------------------------------------------------------------- end to end, host-resident weights
-    e2e = None
-    if not args.no_e2e:
+    def host_model():
+        if host_pack:
+            return host_pack["model"], host_pack["flat"], host_pack["total"]
         names = list(originals)
         total = sum(originals[n].numel() for n in names)
         flat = torch.empty(total, dtype=dtype, pin_memory=True)
-        host_model, host_src, off = ShapeModel(), {}, 0
+        hm, off = ShapeModel(), 0
         for n in names:
             w = originals[n]
             view = flat[off:off + w.numel()].view(w.shape)
@@ -455,135 +590,208 @@ def main():
             off += w.numel()
             lin = nn.Linear(w.shape[1], 1, bias=False)
             lin.weight = nn.Parameter(view, requires_grad=False)
-            host_model.layers[n] = lin
+            hm.layers[n] = lin
         torch.cuda.synchronize()
-        # per-batch statistics arrive on the host, as the reference's hooks produce them (.cpu())
-        stats_host = {K: v.cpu() for K, v in stats_by_K.items()}
-        scale_host = {K: v.cpu() for K, v in act_scale_by_K.items()}
-        host_step = make_step(args.method, acts_by_K, stats_host, scale_host)
-        if args.method == "awq":
-            # the search reads device activations; only the quantize call consumes host statistics
-            import awq_quantizer
+        host_pack.update(model=hm, flat=flat, total=total, src={n: hm.layers[n].weight.data for n in names})
+        return hm, flat, total
 
-            def host_step(m, _acts=acts_by_K):   # noqa: F811
-                tbl = lambda t: {n: t[l.in_features] for n, l in m.named_modules() if isinstance(l, nn.Linear)}  # noqa: E731
-                best = awq_quantizer.awq_search_scale_factor(m, W_BIT, GROUP, tbl(_acts), 0.01, n_grid=N_GRID)
-                awq_quantizer.awq_quantize_model_weight(m, W_BIT, GROUP, tbl(stats_host), 0.01, best)
+    def run_method(method: str):
+        step_fn = make_step(method, acts_by_K, stats_by_K, act_scale_by_K)
 
-        def run_host():
+        def one_step():
+            reset(model, originals)
             if world > 1:
                 with bdist.row_sharded():
-                    host_step(host_model)
-            else:
-                host_step(host_model)
+                    return step_fn(model)
+            return step_fn(model)
 
-        run_host()
+        for _ in range(args.warmup):
+            one_step()
         barrier()
-        n_e2e = max(1, min(args.steps, 2))
-        t0 = time.perf_counter()
-        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        h0.record()
-        for _ in range(n_e2e):
-            run_host()
-        h1.record()
-        torch.cuda.synchronize()
-        wall_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
-        e2e_ms = max(wall_ms, h0.elapsed_time(h1) / n_e2e)
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = _lib.launch_count()
+        _lib.profile_enable(True)
+        bdist.WAIT_EVENTS = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        walker_timings = None
+        if os.environ.get("B200Q_WALKER_TIMINGS") and method == "gptq":
+            import gptq_quantizer as _gq
+            walker_timings = _gq.TIMINGS = []
+        barrier()
+        e0.record()
+        result = None
+        for _ in range(args.steps):
+            result = one_step()
+        e1.record()
+        barrier()
+        if walker_timings is not None:
+            torch.cuda.synchronize()
+            phases = {}
+            for ph, a, b in walker_timings:
+                phases[ph] = phases.get(ph, 0.0) + a.elapsed_time(b) / args.steps
+            print(f"[rank {rank}] walker phases (ms/step): " +
+                  ", ".join(f"{k} {v:.1f}" for k, v in phases.items()), file=sys.stderr, flush=True)
+            _gq.TIMINGS = None
+        _lib.profile_enable(False)
+        ms_total = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        # time the main stream spent waiting for collectives inside the timed steps (b200q.dist
+        # brackets every wait with two events when WAIT_EVENTS is a list) and the bytes they moved
+        nccl_wait_ms = sum(a.elapsed_time(b) for a, b, _n in bdist.WAIT_EVENTS) / args.steps
+        nccl_bytes = sum(n for _a, _b, n in bdist.WAIT_EVENTS) / args.steps
+        bdist.WAIT_EVENTS = None
+        dom_name, dom_bound = DOMINANT[method]
+        kq = {n: _lib.profile_query(n) for n in STAGE_NAMES}
+        kall = _lib.profile_query(None)
+
+        t = torch.tensor([ms_total, nccl_wait_ms], dtype=torch.float64, device=device)
         if world > 1:
             td.all_reduce(t, op=td.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-        passes = 2 if args.method == "awq" else 1      # search + quantize each stream the weights in
-        nbytes = total * flat.element_size()
-        stat_bytes = sum(stats_host[l.in_features].numel() * stats_host[l.in_features].element_size()
-                         for l in host_model.layers.values()) if args.method.startswith(("awq", "gptq")) else 0
-        e2e = {"value": total_rows / (e2e_ms * 1e-3), "unit": "rows/s", "seconds": e2e_ms * 1e-3,
-               "h2d_bytes_per_step": passes * nbytes + stat_bytes, "d2h_bytes_per_step": nbytes,
-               "how": "same entry points on a model whose weights live in pinned host memory: per Linear "
-                      "H2D prefetch / kernels / D2H overlap on three streams (b200q.pipeline); calibration "
-                      "activations stay on the device; wall clock vs CUDA events, the larger"}
-        del host_model, flat
+        ms_step = float(t[0].item()) / args.steps
+        nccl_wait_ms = float(t[1].item())
 
-    if rank != 0:
+        # ------------------------------------------------------------ end to end, host-resident weights
+        e2e = None
+        if not args.no_e2e:
+            hm, flat, total = host_model()
+            # per-batch statistics arrive on the host, as the reference's hooks produce them (.cpu())
+            stats_host = {K: v.cpu() for K, v in stats_by_K.items()}
+            scale_host = {K: v.cpu() for K, v in act_scale_by_K.items()}
+            host_step = make_step(method, acts_by_K, stats_host, scale_host, host=True)
+
+            def run_host():
+                reset(hm, host_pack["src"])
+                if world > 1:
+                    with bdist.row_sharded():
+                        host_step(hm)
+                else:
+                    host_step(hm)
+
+            # the quantized weights overwrite the pinned host tensors in place: restore them
+            # (untimed) so that every timed pass quantizes the original weights
+            def restore():
+                off = 0
+                for n in originals:
+                    w = originals[n]
+                    flat[off:off + w.numel()].view(w.shape).copy_(w)
+                    off += w.numel()
+                torch.cuda.synchronize()
+
+            run_host()
+            n_e2e = max(1, min(args.steps, 2))
+            e2e_ms = 0.0
+            for _ in range(n_e2e):
+                restore()
+                barrier()
+                t0 = time.perf_counter()
+                h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                h0.record()
+                run_host()
+                h1.record()
+                torch.cuda.synchronize()
+                e2e_ms += max((time.perf_counter() - t0) * 1e3, h0.elapsed_time(h1))
+            e2e_ms /= n_e2e
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
+            if world > 1:
+                td.all_reduce(t, op=td.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+            nbytes = total * flat.element_size()
+            stat_bytes = sum(stats_host[l.in_features].numel() * stats_host[l.in_features].element_size()
+                             for l in hm.layers.values()) if method.startswith(("awq", "gptq")) else 0
+            e2e = {"value": total_rows / (e2e_ms * 1e-3), "unit": "rows/s", "seconds": e2e_ms * 1e-3,
+                   "h2d_bytes_per_step": nbytes + stat_bytes, "d2h_bytes_per_step": nbytes,
+                   "how": "same entry points on a model whose weights live in pinned host memory: per Linear "
+                          "H2D prefetch / kernels / D2H overlap on three streams (b200q.pipeline); a "
+                          "search pass keeps its device copies for the quantize pass "
+                          "(pipeline.keep_resident), so each weight crosses PCIe once per direction; "
+                          "calibration activations stay on the device; wall clock vs CUDA events, the larger"}
+
+        roofline = None
+        q = kq[dom_name]
+        if q["launches"] > 0 and q["ms"] > 0:
+            avg_ms = q["ms"] / q["launches"]
+            if dom_bound == "tensor":
+                # timed inside a seconds-long step under the power cap -> sustained bf16 peak
+                peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+                algo = q["flops"] / (q["ms"] * 1e-3) / 1e12
+                # the Gram/Hessian kernel is a SYRK: it runs only the 128x256 tiles that touch the
+                # upper triangle and mirrors them, i.e. it EXECUTES about half of the algorithmic
+                # 2*T*K^2 flops.  The roofline fraction counts the MMAs actually issued.
+                wsum = sum(K * K for _, _, K in layers)
+                exe = sum(K * K * executed_fraction_syrk(K) for _, _, K in layers) / wsum
+                # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel
+                # variant at the same token count (profiles/traffic_r2.json), averaged over layers
+                traffic = None
+                tj = REPO / "profiles" / "traffic_r2.json"
+                if tj.exists() and world == 1:
+                    tr = json.loads(tj.read_text())
+                    byK = tr.get(method, tr).get("dram_bytes_per_launch_by_K", {})
+                    if tr.get("tokens") == tokens_total and all(str(K) in byK for _, _, K in layers):
+                        traffic = sum(byK[str(K)] for _, _, K in layers) / len(layers)
+                roofline = {"bound": "tensor", "kernel": dom_name, "achieved": algo * exe, "peak": peak,
+                            "unit": "TFLOP/s", "frac": algo * exe / peak,
+                            "peak_source": src + ", sustained bf16 (kernel timed inside a long step)",
+                            "traffic": traffic,
+                            "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, "
+                                            "profiles/traffic_r2.json)",
+                            "launches_timed": q["launches"], "avg_launch_ms": avg_ms,
+                            "algorithmic_flops_per_launch": q["flops"] / q["launches"],
+                            "algorithmic_tflops": algo, "executed_mma_fraction": exe,
+                            "note": "achieved = MMAs the kernel issues (SYRK: the 128x256 tiles touching "
+                                    "the upper triangle, mirrored in the epilogue) / CUDA-event time; "
+                                    "algorithmic_tflops = SURVEY 8(d)'s full 2*T*K^2 count over the same time"}
+            else:
+                peak = float(peaks.get("hbm_gbs", 6650.0))
+                ach = q["bytes"] / (q["ms"] * 1e-3) / 1e9
+                roofline = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s",
+                            "frac": ach / peak, "peak_source": src, "traffic": None,
+                            "launches_timed": q["launches"], "avg_launch_ms": avg_ms,
+                            "algorithmic_bytes_per_launch": q["bytes"] / q["launches"]}
+        stages = {n: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                      **({"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12} if v["flops"] > 0 and v["ms"] > 0 else {}),
+                      **({"gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9} if v["bytes"] > 0 and v["ms"] > 0 else {})}
+                  for n, v in kq.items() if v["launches"] > 0}
+        if "awq_search_gemm" in stages and "tflops" in stages["awq_search_gemm"]:
+            # the search GEMM multiplies by H folded onto its lower triangle and stops each output
+            # tile's k-loop at the tile's right edge: it executes about half of the algorithmic flops
+            def tri_fraction(K):
+                tn = -(-K // 256)
+                return sum(min(K, (j + 1) * 256) for j in range(tn)) / (tn * K)
+            wsum = sum(N * K * K for _, N, K in layers)
+            fr = sum(N * K * K * tri_fraction(K) for _, N, K in layers) / wsum
+            stages["awq_search_gemm"]["executed_mma_fraction"] = fr
+            stages["awq_search_gemm"]["executed_tflops"] = stages["awq_search_gemm"]["tflops"] * fr
+        if "spd_inverse" in stages and method == "gptq" and world == 1:
+            stages["spd_inverse"]["note"] = ("inverses of up to 8 layers run concurrently on side streams: "
+                                             "ms_per_step is the SUM of per-stream durations, not wall time")
         if world > 1:
-            td.destroy_process_group()
-        return
+            stages["nccl_exposed"] = {"ms_per_step": nccl_wait_ms, "bytes_per_step_per_rank": nccl_bytes,
+                                      "note": "time the compute stream waited on NCCL work inside the timed "
+                                              "steps (max over ranks) and the payload bytes of this rank's "
+                                              "collectives per step"}
+        cpu = None if (args.no_cpu_baseline or world > 1 or rank != 0) else \
+            cpu_baseline(method, args.model, dtype, tokens_total)
+        return {
+            "metric": metric_of(method), "value": total_rows / (ms_step * 1e-3), "unit": "rows/s",
+            "seconds": ms_step * 1e-3, "ms_per_step": ms_step,
+            "config": config_of(method),
+            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "stages": stages, "kernel_ms_per_step": kall["ms"] / args.steps,
+            "result": result if isinstance(result, float) else None,
+        }
 
-    peaks = json.loads((REPO / "MEASURED_PEAKS.json").read_text()) if (REPO / "MEASURED_PEAKS.json").exists() else {}
-    src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    q = kq[dom_name]
-    roofline = None
-    if q["launches"] > 0 and q["ms"] > 0:
-        avg_ms = q["ms"] / q["launches"]
-        if dom_bound == "tensor":
-            # timed inside a seconds-long step under the power cap -> sustained bf16 peak
-            peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-            ach = q["flops"] / (q["ms"] * 1e-3) / 1e12
-            # the Gram/Hessian kernel is a SYRK: it runs only the 128x256 tiles that touch the upper
-            # triangle and mirrors them, so it EXECUTES about half of the algorithmic 2*T*K^2 flops
-            def executed_fraction(K):
-                tm, tn = -(-K // 128), -(-K // 256)
-                return sum(1 for m in range(tm) for n in range(tn) if (n + 1) * 256 > m * 128) / (tm * tn)
-            wsum = sum(K * K for _, _, K in layers)
-            exe = sum(K * K * executed_fraction(K) for _, _, K in layers) / wsum
-            # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel at
-            # the same token count (profiles/traffic_r1.json), averaged over this model's layers
-            traffic = None
-            tj = REPO / "profiles" / "traffic_r1.json"
-            if tj.exists() and world == 1:
-                tr = json.loads(tj.read_text())
-                byK = tr.get("dram_bytes_per_launch_by_K", {})
-                if tr.get("tokens") == tokens_total and all(str(K) in byK for _, _, K in layers):
-                    traffic = sum(byK[str(K)] for _, _, K in layers) / len(layers)
-            roofline = {"bound": "tensor", "kernel": dom_name, "achieved": ach, "peak": peak,
-                        "unit": "TFLOP/s", "frac": ach / peak,
-                        "peak_source": src + ", sustained bf16 (kernel timed inside a long step)",
-                        "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write)",
-                        "launches_timed": q["launches"], "avg_launch_ms": avg_ms,
-                        "algorithmic_flops_per_launch": q["flops"] / q["launches"],
-                        "executed_mma_fraction": exe, "executed_tflops": ach * exe,
-                        "executed_frac_of_peak": ach * exe / peak,
-                        "note": "achieved = algorithmic 2*T*K^2 flops (SURVEY 8d, full count) / CUDA-event "
-                                "time; X^T X is symmetric and the kernel runs only the tiles touching the "
-                                "upper triangle (mirror-written in the epilogue), so achieved can exceed "
-                                "the GEMM peak; executed_* count the MMAs actually issued"}
-        else:
-            peak = float(peaks.get("hbm_gbs", 6650.0))
-            ach = q["bytes"] / (q["ms"] * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "peak_source": src, "traffic": None,
-                        "launches_timed": q["launches"], "avg_launch_ms": avg_ms,
-                        "algorithmic_bytes_per_launch": q["bytes"] / q["launches"]}
-    stages = {n: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
-                  **({"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12} if v["flops"] > 0 and v["ms"] > 0 else {}),
-                  **({"gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9} if v["bytes"] > 0 and v["ms"] > 0 else {})}
-              for n, v in kq.items() if v["launches"] > 0}
-    if "awq_search_gemm" in stages and "tflops" in stages["awq_search_gemm"]:
-        # the search GEMM multiplies by H folded onto its lower triangle and stops each output
-        # tile's k-loop at the tile's right edge: it executes about half of the algorithmic flops
-        def tri_fraction(K):
-            tn = -(-K // 256)
-            return sum(min(K, (j + 1) * 256) for j in range(tn)) / (tn * K)
-        wsum = sum(N * K * K for _, N, K in layers)
-        fr = sum(N * K * K * tri_fraction(K) for _, N, K in layers) / wsum
-        stages["awq_search_gemm"]["executed_mma_fraction"] = fr
-        stages["awq_search_gemm"]["executed_tflops"] = stages["awq_search_gemm"]["tflops"] * fr
-    # the CPU baseline is a rank-0, single-GPU-run figure (the host cores are shared by all ranks)
-    cpu = None if (args.no_cpu_baseline or world > 1 or rank != 0) else \
-        cpu_baseline(args.method, args.model, dtype, tokens_total)
-    line = {
-        "metric": metric, "value": total_rows / (ms_step * 1e-3), "unit": "rows/s",
-        "seconds": ms_step * 1e-3, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": workload, "linears": len(layers), "rows": total_rows,
-                   "weights": total_elems, "sharding": f"output rows / {world}, calibration samples / {world}",
-                   "l2": "inputs larger than L2 (per-step weight and activation bytes >> 126 MB), no flush"},
-        "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        "stages": stages, "kernel_ms_per_step": kall["ms"] / args.steps,
-        "result": result if isinstance(result, float) else None,
-    }
-    print(json.dumps(line), file=out, flush=True)
+    blocks = {m: run_method(m) for m in methods}
+    if rank == 0:
+        line = dict(blocks[primary])
+        line.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                     "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                     "dtype": args.dtype, "data": "synthetic"})
+        for m in methods[1:]:
+            line[m] = blocks[m]
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         td.destroy_process_group()
 

@@ -25,6 +25,44 @@ import torch.distributed as td
 _active_group = None
 _active = False
 
+# bench.py sets this to a list to learn how long the compute stream sat waiting on collectives:
+# every collective below is then bracketed by two CUDA events on the current stream and recorded as
+# (start, end, payload bytes).  None (the default) costs nothing.
+WAIT_EVENTS = None
+
+
+class _Timed:
+    __slots__ = ("nbytes", "e0")
+
+    def __init__(self, t):
+        self.nbytes = int(t.numel() * t.element_size()) if t is not None else 0
+        self.e0 = None
+
+    def __enter__(self):
+        if WAIT_EVENTS is not None and torch.cuda.is_available():
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None and WAIT_EVENTS is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            WAIT_EVENTS.append((self.e0, e1, self.nbytes))
+        return False
+
+
+class _TimedWork:
+    """Async collective handle whose wait() is bracketed like the synchronous collectives."""
+    __slots__ = ("work", "t")
+
+    def __init__(self, work, t):
+        self.work, self.t = work, t
+
+    def wait(self):
+        with _Timed(self.t):
+            self.work.wait()
+
 
 @contextlib.contextmanager
 def row_sharded(group: Optional["td.ProcessGroup"] = None):
@@ -54,13 +92,15 @@ def rank() -> int:
 
 def allreduce_max(t: torch.Tensor) -> torch.Tensor:
     if is_sharded():
-        td.all_reduce(t, op=td.ReduceOp.MAX, group=_active_group)
+        with _Timed(t):
+            td.all_reduce(t, op=td.ReduceOp.MAX, group=_active_group)
     return t
 
 
 def allreduce_sum(t: torch.Tensor) -> torch.Tensor:
     if is_sharded():
-        td.all_reduce(t, op=td.ReduceOp.SUM, group=_active_group)
+        with _Timed(t):
+            td.all_reduce(t, op=td.ReduceOp.SUM, group=_active_group)
     return t
 
 
@@ -68,14 +108,15 @@ def allreduce_sum_async(t: torch.Tensor):
     """Start the sum over ranks of `t` (in place) and return the work handle, or None when not
     sharded.  handle.wait() orders the caller's current stream after the collective."""
     if is_sharded():
-        return td.all_reduce(t, op=td.ReduceOp.SUM, group=_active_group, async_op=True)
+        return _TimedWork(td.all_reduce(t, op=td.ReduceOp.SUM, group=_active_group, async_op=True), t)
     return None
 
 
 def broadcast(t: torch.Tensor, src: int = 0) -> torch.Tensor:
     if is_sharded():
-        td.broadcast(t, src=td.get_global_rank(_active_group, src) if _active_group else src,
-                     group=_active_group)
+        with _Timed(t):
+            td.broadcast(t, src=td.get_global_rank(_active_group, src) if _active_group else src,
+                         group=_active_group)
     return t
 
 
@@ -89,7 +130,8 @@ def gather_rows(compute, n_rows: int, row_shape, dtype, device) -> torch.Tensor:
     per = n_rows // w
     local = compute(r * per, (r + 1) * per).contiguous()
     out = torch.empty((n_rows, *row_shape), dtype=dtype, device=device)
-    td.all_gather_into_tensor(out, local, group=_active_group)
+    with _Timed(out):
+        td.all_gather_into_tensor(out, local, group=_active_group)
     return out
 
 

@@ -24,6 +24,41 @@ from . import ops as _ops
 
 Compute = Callable[[str, nn.Linear, torch.Tensor], Optional[torch.Tensor]]
 
+# ---- device copies kept between passes over HOST-resident weights --------------------------------
+# A search pass followed by a quantize pass (awq_search_scale_factor -> awq_quantize_model_weight)
+# would stream every weight host -> device twice.  Inside `with keep_resident():` the device copy a
+# READ-ONLY pass made of a host weight is kept (up to a byte budget) and the next pass over the
+# same, unmodified host tensor uses it instead of copying again; a pass that writes a layer drops
+# that layer's copy.  Opt-in and scoped: nothing is cached outside the block.
+_resident = None     # {key: device tensor} while a keep_resident() block is active
+_resident_budget = 0
+_resident_bytes = 0
+
+
+def _key(w: torch.Tensor):
+    return (w.data_ptr(), tuple(w.shape), w.dtype, w._version)
+
+
+class keep_resident:
+    def __init__(self, max_bytes: Optional[int] = None):
+        self.max_bytes = max_bytes
+
+    def __enter__(self):
+        global _resident, _resident_budget, _resident_bytes
+        self._prev = (_resident, _resident_budget, _resident_bytes)
+        budget = self.max_bytes
+        if budget is None and torch.cuda.is_available():
+            free, _total = torch.cuda.mem_get_info()
+            budget = int(free * 0.5)          # leave half of what is free now to the kernels' scratch
+        _resident, _resident_budget, _resident_bytes = {}, int(budget or 0), 0
+        return self
+
+    def __exit__(self, *exc):
+        global _resident, _resident_budget, _resident_bytes
+        _resident, _resident_budget, _resident_bytes = self._prev
+        return False
+
+
 
 def _assign(module: nn.Linear, out: torch.Tensor) -> None:
     module.weight.data = out
@@ -46,6 +81,24 @@ def run_layers(items: Sequence[Tuple[str, nn.Linear]], compute: Compute) -> None
     _run_host_layers(items, compute)
 
 
+def _remember(key, W: torch.Tensor) -> None:
+    global _resident_bytes
+    if _resident is None or key is None or key in _resident:
+        return
+    nbytes = W.numel() * W.element_size()
+    if _resident_bytes + nbytes <= _resident_budget:
+        _resident[key] = W
+        _resident_bytes += nbytes
+
+
+def _forget(key) -> None:
+    global _resident_bytes
+    if _resident is not None and key is not None:
+        W = _resident.pop(key, None)
+        if W is not None:
+            _resident_bytes -= W.numel() * W.element_size()
+
+
 def _run_host_layers(items: List[Tuple[str, nn.Linear]], compute: Compute) -> None:
     dev = torch.device("cuda", torch.cuda.current_device())
     cur = torch.cuda.current_stream(dev)
@@ -54,12 +107,19 @@ def _run_host_layers(items: List[Tuple[str, nn.Linear]], compute: Compute) -> No
     n = len(items)
     staged = [None] * n
     ready = [None] * n
+    keys = [None] * n
 
     def prefetch(i: int) -> None:
         w = items[i][1].weight.data
         if w.is_cuda:
             staged[i] = w.contiguous()
             return
+        if _resident is not None:
+            hit = _resident.get(_key(w))
+            if hit is not None:
+                staged[i], keys[i] = hit, _key(w)
+                return
+        keys[i] = _key(w)
         if i == 0:
             h2d.wait_stream(cur)
         with torch.cuda.stream(h2d):
@@ -81,7 +141,9 @@ def _run_host_layers(items: List[Tuple[str, nn.Linear]], compute: Compute) -> No
         staged[i] = None
         out = compute(name, m, W)
         if out is None:
+            _remember(keys[i], W)           # read-only pass: the copy may serve the next pass
             continue
+        _forget(keys[i])                    # the host tensor is about to change
         host = m.weight.data
         if host.is_cuda:
             _assign(m, out)

@@ -403,11 +403,13 @@ group128_kernel(const T* __restrict__ W, T* __restrict__ out, GroupQuantArgs a) 
 #pragma unroll
         for (int e = 1; e < 16; ++e) { mx = fmaxf(mx, x[e]); mn = fminf(mn, x[e]); }
       }
-      // this branch is taken by whole 8-lane teams, so a width-8 shuffle is well defined
+      // this branch is taken by whole 8-lane teams: name the team explicitly (under independent
+      // thread scheduling __activemask() need not contain all eight lanes at this point)
+      const unsigned team = 0xffu << (sub * 8);
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) {
-        mx = fmaxf(mx, __shfl_xor_sync(__activemask(), mx, o, 8));
-        if constexpr (!SYM) mn = fminf(mn, __shfl_xor_sync(__activemask(), mn, o, 8));
+        mx = fmaxf(mx, __shfl_xor_sync(team, mx, o, 8));
+        if constexpr (!SYM) mn = fminf(mn, __shfl_xor_sync(team, mn, o, 8));
       }
       quantize_group16<T, SYM, COLOP, true>(x, cv, cr, mx, mn, a, scale, zp, code);
     }

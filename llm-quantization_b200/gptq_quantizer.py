@@ -185,7 +185,7 @@ def gptq_quantize_model_weight(
 
     def compute(name, _module, W):
         if name not in input_feat:
-            return _ops.group_fakequant(W, w_bit, q_group_size, symmetric=True)
+            return _symmetric_groups(W, w_bit, q_group_size)
         if name not in ready:
             i = position[name]
             world = _dist.world_size()
@@ -254,8 +254,18 @@ def _simple_quantize_layer(layer: nn.Linear, n_bit: int, q_group_size: int) -> N
     """Symmetric |max| group quantization, codes in [-2^b, 2^b-1] (reference: :79-108)."""
     w = layer.weight.data
     src = w.device
-    out = _ops.group_fakequant(_ops.to_device(w), n_bit, q_group_size, symmetric=True)
+    out = _symmetric_groups(_ops.to_device(w), n_bit, q_group_size)
     layer.weight.data = out if out.device == src else out.to(src)
+
+
+def _symmetric_groups(W: torch.Tensor, n_bit: int, q_group_size: int) -> torch.Tensor:
+    """The reference groups with `w.reshape(-1, q_group_size)` (:88-91): consecutive elements of
+    the FLATTENED weight, so a group size that does not divide in_features is still legal as long
+    as it divides the element count -- groups then run across row boundaries."""
+    if q_group_size > 0 and W.shape[-1] % q_group_size != 0:
+        flat = W.reshape(-1, q_group_size)          # raises like the reference if numel % G != 0
+        return _ops.group_fakequant(flat, n_bit, -1, symmetric=True).reshape(W.shape)
+    return _ops.group_fakequant(W, n_bit, q_group_size, symmetric=True)
 
 
 @torch.no_grad()
@@ -300,6 +310,14 @@ def _hessian_stage(input_feat, K: int, device, perp_damp: float, nsamples: int):
     if MODE not in ("parity", "compensated"):
         raise ValueError(f"gptq_quantizer.MODE must be 'parity' or 'compensated', got {MODE!r}")
     if MODE == "parity" and not BUILD_HESSIAN:
+        return None
+    if K % 8 != 0:
+        # the tensor-core Hessian kernel reads the activations by TMA (16-byte row pitch)
+        if MODE == "compensated":
+            raise NotImplementedError(f"compensated GPTQ needs in_features % 8 == 0, got {K}")
+        import warnings
+        warnings.warn(f"gptq: in_features = {K} is not a multiple of 8; H and H^-1 (which the "
+                      f"reference-parity output does not read) are not built for this layer")
         return None
     return gptq_hessian(input_feat, K, device, perp_damp, nsamples)
 

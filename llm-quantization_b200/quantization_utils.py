@@ -50,7 +50,12 @@ def pseudo_quantize_tensor(w: Tensor, n_bit: int = 4, q_group_size: int = -1) ->
     else:
         assert w.dim() == 2
     src = w.device
-    out = _ops.group_fakequant(_ops.to_device(w), n_bit, q_group_size)
+    wd = _ops.to_device(w)
+    out = _ops.group_fakequant(wd, n_bit, q_group_size)
+    # The reference asserts that neither the scales nor the result contain NaN (:398-399, :407).
+    # The kernel's min/max and clamps drop NaNs (a NaN weight would come out as a finite grid
+    # point), so the contract is kept by testing the INPUT: NaN in <=> NaN scales in the reference.
+    assert torch.isnan(wd).sum() == 0
     return out if src == out.device else out.to(src)
 
 

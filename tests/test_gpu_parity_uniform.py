@@ -330,3 +330,35 @@ def test_shape_errors_are_assertions():
         pseudo_quantize_tensor(torch.randn(4, 100), n_bit=4, q_group_size=32)
     with pytest.raises(AssertionError):
         pseudo_quantize_tensor(torch.randn(2, 4, 8), n_bit=4, q_group_size=-1)
+
+
+def test_gptq_boundary_cases_the_reference_accepts():
+    """in_features not a multiple of 8 (H cannot be built by the TMA-fed kernel: parity output does
+    not need it), and a symmetric-fallback group size that divides the element count but not
+    in_features (the reference's reshape(-1, G), gptq_quantizer.py:88-91)."""
+    import warnings
+    import torch.nn as nn
+    import gptq_quantizer as gq
+    from oracle import quant_oracle as O
+    g = torch.Generator().manual_seed(11)
+    w = torch.randn(48, 100, generator=g) * 0.02
+    lin = nn.Linear(100, 48, bias=False)
+    lin.weight.data = w.clone().cuda()
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        gq._gptq_quantize_layer(lin, 4, 128, [torch.randn(16, 100, generator=g) for _ in range(3)],
+                                verbose=False)
+    assert any("not a multiple of 8" in str(x.message) for x in rec)
+    assert torch.equal(lin.weight.data.cpu(), O.gptq_parity_quant(w, 4)["out"])
+    # 48 x 100 = 4800 elements in groups of 64: groups straddle rows
+    lin.weight.data = w.clone().cuda()
+    gq._simple_quantize_layer(lin, 4, 64)
+    assert torch.equal(lin.weight.data.cpu(), O.symmetric_group_quant(w, 4, 64)["out"])
+
+
+def test_pseudo_quantize_rejects_nan_like_the_reference():
+    from quantization_utils import pseudo_quantize_tensor
+    w = torch.randn(8, 128)
+    w[3, 5] = float("nan")
+    with pytest.raises(AssertionError):
+        pseudo_quantize_tensor(w.cuda(), 4, 128)
