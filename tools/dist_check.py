@@ -115,7 +115,38 @@ with torch.no_grad():
         results[f"grouped gptq walker, {mode}: sharded vs unsharded agreement {agree:.5f}"] = \
             agree == 1.0 if mode == "parity" else agree >= 0.999
     gptq_quantizer.MODE = "parity"
+    # Llama-3-8B k/v projection shape (BASELINE configs[2]): N = 1024 -> 128 rows per rank at 8
+    # GPUs, K = 4096 (tensor-core inverse path), w3 act-order, parity and compensated
+    Nkv, Kkv = 1024, 4096
+    Wkv = torch.randn(Nkv, Kkv, generator=gg) * 0.02
+    chan_kv = torch.ones(Kkv); chan_kv[torch.randperm(Kkv, generator=gg)[:40]] = 20.0
+    acts_kv = {"0": [(torch.randn(256, Kkv, generator=gg) * chan_kv).to(torch.bfloat16).to(dev) for _ in range(8)]}
+    k0, k1 = D.shard_rows(Nkv, world, rank)
+    def kv(rows):
+        net = nn.Sequential(nn.Linear(Kkv, 1, bias=False)).to(dev)
+        net[0].weight.data = Wkv[rows].clone().to(dev)
+        return net
+    def gather_kv(t):
+        parts = [torch.empty((D.shard_rows(Nkv, world, r)[1] - D.shard_rows(Nkv, world, r)[0], Kkv), device=dev)
+                 for r in range(world)]
+        td.all_gather(parts, t.contiguous())
+        return torch.cat(parts).cpu()
+    for mode in ("parity", "compensated"):
+        gptq_quantizer.MODE = mode
+        sh = kv(slice(k0, k1))
+        with D.row_sharded():
+            gptq_quantizer.gptq_quantize_model_weight(sh, 3, 128, acts_kv, actorder=True, verbose=False)
+        full = kv(slice(0, Nkv))
+        gptq_quantizer.gptq_quantize_model_weight(full, 3, 128, acts_kv, actorder=True, verbose=False)
+        got = gather_kv(sh[0].weight.data)
+        agree = (got == full[0].weight.data.cpu()).float().mean().item()
+        ok = agree == 1.0 if mode == "parity" else agree >= 0.999
+        if mode == "parity":
+            ok = ok and torch.equal(got, O.gptq_parity_quant(Wkv, 3)["out"])
+        results[f"llama3 k/v 1024x4096 w3 act-order, {mode}: {k1 - k0} rows/rank, agreement {agree:.5f}"] = ok
+    gptq_quantizer.MODE = "parity"
 if rank == 0:
+    print(f"dist_check: {world} ranks on {torch.cuda.get_device_name(0)}, NCCL {'.'.join(map(str, torch.cuda.nccl.version()))}")
     for k, v in results.items():
         print(("PASS " if v else "FAIL ") + k)
     print("ALL PASS" if all(results.values()) else "SOME FAILED")
