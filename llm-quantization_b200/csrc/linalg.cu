@@ -722,9 +722,12 @@ int64_t b200q_gptq_compensated_workspace(int64_t N, int64_t K) {
 
 // W (fp32 [N,K], destroyed) -> Q (fp32 [N,K]) with U = upper Cholesky factor of H^-1.
 // group: any size dividing K, or <= 0 (one group per row); 128 takes the register-only fast path.
-// blocksize: the lazy-update batch of Alg. 1.  It only regroups the SAME rank-1 updates (the
-// result is mathematically independent of it), so any positive value is accepted and the kernel
-// batches by its native 128 columns.
+// blocksize: the lazy-update batch of Alg. 1.  Values up to 128 are honoured exactly (the kernel
+// takes that many columns per launch).  Larger values batch by 128: the lazy update only regroups
+// the SAME rank-1 updates, so the result differs from a true larger batch only where a quantisation
+// group straddles a batch boundary and its (min, max) is taken over columns that have / have not
+// yet received the pending updates (group sizes dividing 128, or multiples of the blocksize, are
+// unaffected).
 int b200q_gptq_compensated(float* W, float* Q, const float* U, int64_t N, int64_t K, int64_t group,
                            int n_bit, int blocksize, void* work, void* stream) {
   B200Q_REQUIRE(W && Q && U && work && N > 0 && K > 0, "gptq_compensated: bad argument");
@@ -752,9 +755,10 @@ int b200q_gptq_compensated(float* W, float* Q, const float* U, int64_t N, int64_
   SplitOperand ut;
   int rc = split_operand(st, U, K, (int)K, (int)K, true, 2, planes_u, &ut);
   if (rc != B200Q_OK) return rc;
-  for (int64_t c0 = 0; c0 < K; c0 += gc::B) {
-    const int nb = (int)std::min<int64_t>(gc::B, K - c0);
-    if (G == gc::B) {
+  const int step = std::min(blocksize, gc::B);
+  for (int64_t c0 = 0; c0 < K; c0 += step) {
+    const int nb = (int)std::min<int64_t>(step, K - c0);
+    if (G == gc::B && step == gc::B) {
       gptq_block_kernel<0><<<blocks, 256, smem, st>>>(W, Q, Err, U, N, K, c0, nb, maxint, G, nullptr,
                                                       nullptr);
     } else {

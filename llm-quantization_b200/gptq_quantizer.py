@@ -36,7 +36,8 @@ from b200q import pipeline as _pipeline  # noqa: E402
 MODE = "parity"
 BUILD_HESSIAN = True
 GROUP_FACTOR = 4    # under row sharding, layers prepared together = GROUP_FACTOR * world size
-FACTOR_STREAMS = 8  # one GPU: Hessian inverses in flight at a time (each on its own CUDA stream)
+FACTOR_STREAMS = 16 # Hessian inverses in flight at a time on one GPU (each on its own CUDA stream)
+LOCAL_GROUP = 16    # one GPU: layers prepared together (Hessians, then their inverses side by side)
 TIMINGS = None      # set to a list to collect (phase, ms) CUDA-event pairs from the model walker
 
 
@@ -101,7 +102,7 @@ def gptq_quantize_model_weight(
     calibrated = [(n, m) for n, m in items if n in input_feat]
     position = {n: i for i, (n, _) in enumerate(calibrated)}
     ready: Dict[str, _Prepared] = {}
-    retiring: List[_Prepared] = []          # previous group: inverses possibly still in flight
+    retiring: List[_Prepared] = []          # status flags not yet looked at (checked one group late)
     side_streams: List[torch.cuda.Stream] = []
 
     def retire():
@@ -109,66 +110,32 @@ def gptq_quantize_model_weight(
             p.check()
         retiring.clear()
 
-    def prepare_sharded(group, device):
-        # Under row sharding the inverse of one layer's Hessian is a single-GPU job, so a GROUP
-        # of layers is prepared at once: every rank adds its calibration samples to each
-        # layer's Hessian (all-reduced), then the ranks factor DIFFERENT layers of the group at
-        # the same time (dealt longest-first by K^3, so a rank that draws an 11008-wide layer
-        # gets fewer 4096-wide ones), and the factors are broadcast.
-        world = _dist.world_size()
-        owner = _deal_layers([(n, m.weight.shape[1]) for n, m in group], world)
-        # three phases, so that no collective sits between two ranks' factorisations (an
-        # all-reduce there would make everybody wait for whoever is busy inverting)
-        t0 = _mark()
-        hessians = [_hessian_stage(input_feat[n], m.weight.shape[1], device, perp_damp, nsamples)
-                    for n, m in group]
-        t1 = _mark()
-        prepared = [_factor_stage(n, H, actorder, owner[n]) for (n, _m), H in zip(group, hessians)]
-        t2 = _mark()
-        flags = []
-        for p in prepared:
-            if p.factor is not None:
-                _dist.broadcast(p.factor, owner[p.name])
-                flags.append(p.info)
-        if flags:
-            # one status exchange and one host sync for the whole group: every rank sees every
-            # owner's flag, so all ranks warn / raise together
-            status = _dist.allreduce_max(torch.cat(flags))
-            for p, j in zip([p for p in prepared if p.factor is not None], status.tolist()):
-                p.info = None
-                _report_pivot(int(j), p.K, p.name)
-        for p in prepared:
-            ready[p.name] = p
-        _lap("hessians", t0, t1)
-        _lap("factors", t1, t2)
-        _lap("broadcast", t2, _mark())
-
-    def prepare_local(group, device):
-        # One GPU: a factorisation is a chain of ~500 small dependent kernels that keeps a few SMs
-        # busy (linalg.cu), so the inverses of a group of layers run CONCURRENTLY, each on its own
-        # stream, while the main stream goes on with the column stages of this group and the
-        # Hessian GEMMs of the next one.  Order of events for group g:
-        #   main : H(g)[0..n)  -> [wait: inverses of g-1 done, flags checked]  -> columns(g) ...
-        #   side k:            wait H(g)[k] -> inverse -> flag to pinned host memory -> done[k]
+    def factor_concurrently(jobs, device):
+        """jobs: [(name, H, owner)].  A factorisation is a chain of ~500 small dependent kernels
+        (64-column diagonal blocks, leaf GEMMs, operand splits: linalg.cu) that keeps only a few
+        SMs busy, and the layers of a group are independent: the ones this rank owns run
+        CONCURRENTLY, each on its own CUDA stream, with the GPU to themselves (the Hessian GEMMs
+        occupy every SM's shared memory, so the two phases are not interleaved); the main stream
+        waits for all of them.  Status flags travel to pinned host memory and are read one group
+        later (no host sync on the critical path)."""
         main = torch.cuda.current_stream(device)
-        t0 = _mark()
-        hessians, built = [], []
-        for n, m in group:
-            hessians.append(_hessian_stage(input_feat[n], m.weight.shape[1], device, perp_damp, nsamples))
-            built.append(torch.cuda.Event())
-            built[-1].record(main)
-        t1 = _mark()
-        retire()                      # the previous group's inverses ran under this group's Hessians
-        while len(side_streams) < min(FACTOR_STREAMS, len(group)):
+        mine = [j for j in jobs if j[1] is not None and (not _dist.is_sharded() or _dist.rank() == j[2])]
+        n_streams = _factor_stream_count(max((j[1].shape[0] for j in mine), default=0), len(mine), device)
+        while len(side_streams) < n_streams:
             side_streams.append(torch.cuda.Stream(device))
-        for k, ((n, m), H) in enumerate(zip(group, hessians)):
-            if H is None:
-                ready[n] = _Prepared(n, None, None, None, m.weight.shape[1])
+        start = torch.cuda.Event()
+        start.record(main)
+        out, k = [], 0
+        for name, H, owner in jobs:
+            if H is None or n_streams <= 1 or (_dist.is_sharded() and _dist.rank() != owner):
+                out.append(_factor_stage(name, H, actorder, owner))     # inline (or a placeholder)
                 continue
-            side = side_streams[k % len(side_streams)]
-            side.wait_event(built[k])
+            side = side_streams[k % n_streams]
+            k += 1
+            if k <= n_streams:
+                side.wait_event(start)
             with torch.cuda.stream(side):
-                p = _factor_stage(n, H, actorder, 0)
+                p = _factor_stage(name, H, actorder, owner)
                 p.info_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
                 p.info_host.copy_(p.info, non_blocking=True)
                 p.done = torch.cuda.Event()
@@ -176,12 +143,50 @@ def gptq_quantize_model_weight(
             # memory handed across streams: H is read by the side stream, the factor (allocated
             # there) by the main stream
             H.record_stream(side)
-            for t in (p.factor, p.perm):
+            for t in (p.factor, p.perm, p.info):
                 if t is not None:
                     t.record_stream(main)
-            ready[n] = p
+            out.append(p)
+        for p in out:
+            if p.done is not None:
+                main.wait_event(p.done)
+        return out
+
+    def prepare(group, device):
+        # A GROUP of layers is prepared at once.  Under row sharding every rank adds its calibration
+        # samples to each layer's Hessian (all-reduced), then the ranks factor DIFFERENT layers of
+        # the group at the same time (dealt longest-first by K^3, so a rank that draws an
+        # 11008-wide layer gets fewer 4096-wide ones) and the factors are broadcast.  Three phases,
+        # so that no collective sits between two ranks' factorisations (an all-reduce there would
+        # make everybody wait for whoever is busy inverting).
+        world = _dist.world_size()
+        owner = _deal_layers([(n, m.weight.shape[1]) for n, m in group], world)
+        t0 = _mark()
+        hessians = [_hessian_stage(input_feat[n], m.weight.shape[1], device, perp_damp, nsamples)
+                    for n, m in group]
+        t1 = _mark()
+        retire()                      # the previous group's flags: long since on the host
+        prepared = factor_concurrently([(n, H, owner[n]) for (n, _m), H in zip(group, hessians)], device)
+        t2 = _mark()
+        if world > 1:
+            flags = []
+            for p in prepared:
+                if p.factor is not None:
+                    _dist.broadcast(p.factor, owner[p.name])
+                    flags.append(p.info)
+                    p.done = p.info_host = None
+            if flags:
+                # one status exchange and one host sync for the whole group: every rank sees every
+                # owner's flag, so all ranks warn / raise together
+                status = _dist.allreduce_max(torch.cat(flags))
+                for p, j in zip([p for p in prepared if p.factor is not None], status.tolist()):
+                    p.info = None
+                    _report_pivot(int(j), p.K, p.name)
+        for p in prepared:
+            ready[p.name] = p
         _lap("hessians", t0, t1)
-        _lap("factors(launch)", t1, _mark())
+        _lap("factors", t1, t2)
+        _lap("broadcast", t2, _mark())
 
     def compute(name, _module, W):
         if name not in input_feat:
@@ -189,18 +194,14 @@ def gptq_quantize_model_weight(
         if name not in ready:
             i = position[name]
             world = _dist.world_size()
-            if world > 1:
-                prepare_sharded(calibrated[i:i + GROUP_FACTOR * world], W.device)
-            else:
-                prepare_local(calibrated[i:i + max(1, FACTOR_STREAMS)], W.device)
+            prepare(calibrated[i:i + (GROUP_FACTOR * world if world > 1 else max(1, LOCAL_GROUP))],
+                    W.device)
         p = ready.pop(name)
-        if p.done is not None:
+        if p.done is not None or p.info_host is not None:
             if MODE == "compensated":
-                # the column stage multiplies by the factor: it must be finished and sound
-                torch.cuda.current_stream(W.device).wait_event(p.done)
-                p.check()
+                p.check()             # the column stage multiplies by the factor: it must be sound
             else:
-                retiring.append(p)    # parity output does not read H^-1: join at the group boundary
+                retiring.append(p)    # parity output does not read H^-1: look at the flag later
         t2 = _mark()
         out = _column_stage(W, w_bit, q_group_size, blocksize, p.H, p.perm, p.factor)
         _lap("columns", t2, _mark())
@@ -209,15 +210,21 @@ def gptq_quantize_model_weight(
     try:
         _pipeline.run_layers(items, compute)
     finally:
-        for p in list(ready.values()):
-            retiring.append(p)
+        retiring.extend(ready.values())
         ready.clear()
-        if retiring:
-            main = torch.cuda.current_stream()
-            for p in retiring:
-                if p.done is not None:
-                    main.wait_event(p.done)
-            retire()
+        retire()
+
+
+def _factor_stream_count(K: int, n_jobs: int, device) -> int:
+    """Factorisations in flight at once on this GPU: FACTOR_STREAMS, fewer when their workspaces
+    (3 K^2 floats + fp16 operand planes each, cached per stream) would not fit in half of the free
+    memory."""
+    if n_jobs <= 1 or K <= 0:
+        return min(1, n_jobs)
+    from b200q import _lib as _l
+    per = _l.load().b200q_spd_inverse_workspace(K) + 3 * 4 * K * K
+    free, _total = torch.cuda.mem_get_info(device)
+    return int(max(1, min(FACTOR_STREAMS, n_jobs, (free // 2) // max(per, 1))))
 
 
 def _deal_layers(layers, world: int) -> Dict[str, int]:

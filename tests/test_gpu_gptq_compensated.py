@@ -44,7 +44,8 @@ def out_err(Wq, W, feats):
                                             # admits (gptq_quantizer.py:22-32): 32, 64, straddling
                                             # 192, and lazy batches other than the kernel's own 128
                                             (64, 256, 4, 64, False, 128), (40, 384, 4, 32, True, 64),
-                                            (32, 384, 3, 192, False, 256), (48, 512, 4, 128, True, 32)])
+                                            (32, 384, 3, 192, False, 64), (48, 512, 4, 128, True, 32),
+                                            (32, 384, 3, 192, False, 128), (48, 512, 4, 256, False, 256)])
 def test_compensated_matches_fp64_oracle(N, K, b, G, act, bs):
     import gptq_quantizer as gq
     from b200q import tensor_ops as T
