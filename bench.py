@@ -52,6 +52,10 @@ for _p in (str(REPO / "llm-quantization_b200"), str(REPO)):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+# the GPTQ walker runs up to 16 Hessian inverses side by side on their own streams: give them their
+# own hardware work queues (the default of 8 makes streams share queues and serialise)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import torch  # noqa: E402
 import torch.nn as nn  # noqa: E402
 
@@ -619,6 +623,8 @@ def main():
         if os.environ.get("B200Q_WALKER_TIMINGS") and method == "gptq":
             import gptq_quantizer as _gq
             walker_timings = _gq.TIMINGS = []
+            _gq.HOST_LAPS = {}
+            _gq.TRACE = []
         barrier()
         e0.record()
         result = None
@@ -633,7 +639,17 @@ def main():
                 phases[ph] = phases.get(ph, 0.0) + a.elapsed_time(b) / args.steps
             print(f"[rank {rank}] walker phases (ms/step): " +
                   ", ".join(f"{k} {v:.1f}" for k, v in phases.items()), file=sys.stderr, flush=True)
-            _gq.TIMINGS = None
+            print(f"[rank {rank}] walker host seconds per step: " +
+                  ", ".join(f"{k} {v / args.steps:.3f}" for k, v in _gq.HOST_LAPS.items()),
+                  file=sys.stderr, flush=True)
+            last = None
+            for g0, b, e, K in _gq.TRACE[:16 * 3] + _gq.TRACE[-16 * 4:-16 * 2]:
+                if last is not g0:
+                    print(f"[trace] group of K={K}:", file=sys.stderr)
+                    last = g0
+                print(f"[trace]   begin +{g0.elapsed_time(b):8.2f} ms  end +{g0.elapsed_time(e):8.2f} ms",
+                      file=sys.stderr)
+            _gq.TIMINGS = _gq.HOST_LAPS = _gq.TRACE = None
         _lib.profile_enable(False)
         ms_total = e0.elapsed_time(e1)
         launches = _lib.launch_count() - launches0

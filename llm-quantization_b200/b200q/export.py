@@ -75,6 +75,61 @@ def export_gptq_parity(W: torch.Tensor, n_bit: int) -> Dict:
             "scales": scales}
 
 
+def _bit_plane(mask: torch.Tensor) -> torch.Tensor:
+    return pack_codes(mask.to(torch.uint8).contiguous(), 1)
+
+
+def export_pot(W: torch.Tensor, n_bit: int, group: int) -> Dict:
+    """`pot_quantize_tensor` (pot_apot_quantizer.py:25-115) with the integers kept.  Every value is
+    s * sign(w) * 2^E (:104-107): the code of an element is E (n_bit - 1 bits, E in
+    [0, 2^(n_bit-1) - 1]) with the sign in the top bit, packed at n_bit bits; one fp32 scale per
+    group (the winning point of the 200-candidate search, `grid_index` says which).  sign(0) = 0
+    makes exact zeros a 2^n_bit + 1-th symbol: they are kept as a 1-bit plane, present only when the
+    tensor contains one."""
+    W = _ops.to_device(W)
+    K = W.shape[-1]
+    G = group if group > 0 else K
+    assert K % G == 0
+    groups = W.reshape(-1, G)
+    out, exps, scale, idx = _ops.pot_quant(groups, n_bit, torch.arange(0.01, 2.01, 0.01), return_codes=True)
+    neg = torch.signbit(out) & (out != 0)
+    codes = exps | (neg.to(torch.uint8) << (n_bit - 1))
+    zero = out == 0
+    rec = {"scheme": "pot", "bits": n_bit, "group": G, "shape": tuple(W.shape),
+           "dtype": str(W.dtype).replace("torch.", ""),
+           "qweight": pack_codes(codes.reshape(-1, K), n_bit), "scales": scale, "grid_index": idx}
+    if bool(zero.any()):
+        rec["zero_mask"] = _bit_plane(zero.reshape(-1, K))
+    return rec
+
+
+def export_apot(W: torch.Tensor, n_bit: int, group: int, k: int = 2, total_elements: int = None) -> Dict:
+    """`apot_quantize_tensor` (pot_apot_quantizer.py:192-351) with the integers kept.  Every value
+    is s * level[i] (:294-298, :331-340): the code is the index i into the signed level table
+    (31 entries at w4 k2, at most 32), packed at ceil(log2(#levels)) bits; one fp32 scale per group;
+    the table itself travels in the record.  total_elements = element count of the whole tensor when
+    W is a row shard (it selects the 20- or 40-point grid, :258-262)."""
+    import sys
+    from pathlib import Path
+    pkg = str(Path(__file__).resolve().parent.parent)
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    from pot_apot_quantizer import _apot_signed_levels
+    W = _ops.to_device(W)
+    K = W.shape[-1]
+    G = group if group > 0 else K
+    assert K % G == 0
+    groups = W.reshape(-1, G)
+    levels = _apot_signed_levels(n_bit, k)
+    total = W.numel() if total_elements is None else int(total_elements)
+    grid = torch.arange(0.01, 2.01, 0.1 if total > 500000 else 0.05)
+    out, lidx, scale, idx = _ops.apot_quant(groups, levels, grid, return_codes=True)
+    bits = max(1, (levels.numel() - 1).bit_length())
+    return {"scheme": "apot", "bits": bits, "group": G, "shape": tuple(W.shape),
+            "dtype": str(W.dtype).replace("torch.", ""), "levels": levels.to(W.device),
+            "qweight": pack_codes(lidx.reshape(-1, K), bits), "scales": scale, "grid_index": idx}
+
+
 def dequantize(record: Dict) -> torch.Tensor:
     """The fake-quantized weight a record stands for, in the record's dtype."""
     shape = tuple(record["shape"])
@@ -91,6 +146,22 @@ def dequantize(record: Dict) -> torch.Tensor:
     elif record["scheme"] == "gptq_column_sym":
         q = (codes - float(record["offset"])).to(dtype)
         w = q * record["scales"].reshape(1, K).to(dtype)          # gptq_quantizer.py:186
+    elif record["scheme"] == "pot":
+        G, b = record["group"], record["bits"]
+        c = codes.to(torch.int32).reshape(-1, G)
+        E = (c & ((1 << (b - 1)) - 1)).to(dtype)
+        sign = torch.where((c >> (b - 1)) != 0, -1.0, 1.0).to(dtype)
+        # scale * sign * 2^E (pot_apot_quantizer.py:105-107): powers of two, exact in any order
+        w = record["scales"].reshape(-1, 1).to(dtype) * sign * torch.pow(torch.tensor(2.0, dtype=dtype, device=c.device), E)
+        if "zero_mask" in record:
+            z = unpack_codes(record["zero_mask"], K, 1).reshape(-1, G).bool()
+            w = torch.where(z, torch.zeros((), dtype=dtype, device=w.device), w)
+    elif record["scheme"] == "apot":
+        G = record["group"]
+        idx = codes.long().reshape(-1, G)
+        # scale (a value of the weight's dtype) times the fp32 level, one rounding, then the cast
+        # back to the weight's dtype (pot_apot_quantizer.py:335-340)
+        w = (record["scales"].reshape(-1, 1).float() * record["levels"].float()[idx]).to(dtype)
     else:
         raise ValueError(f"unknown scheme {record['scheme']!r}")
     return w.reshape(shape)
@@ -104,11 +175,14 @@ FORMAT_VERSION = 1
 
 def export_model(model, n_bit: int, group: int, scheme: str = "uniform_asym") -> Dict[str, Dict]:
     """{module name: record} for every nn.Linear of `model` (weights may live on the host; they are
-    streamed through the GPU).  scheme: "uniform_asym" (pseudo_quantize_tensor) or
-    "gptq_column_sym" (the reference's GPTQ column stage)."""
+    streamed through the GPU).  scheme: "uniform_asym" (pseudo_quantize_tensor),
+    "gptq_column_sym" (the reference's GPTQ column stage), "pot" or "apot" (exponent / level-index
+    planes of pot_apot_quantizer.py)."""
     import torch.nn as nn
     fn = {"uniform_asym": lambda w: export_uniform(w, n_bit, group),
-          "gptq_column_sym": lambda w: export_gptq_parity(w, n_bit)}.get(scheme)
+          "gptq_column_sym": lambda w: export_gptq_parity(w, n_bit),
+          "pot": lambda w: export_pot(w, n_bit, group),
+          "apot": lambda w: export_apot(w, n_bit, group)}.get(scheme)
     if fn is None:
         raise ValueError(f"unknown scheme {scheme!r}")
     return {name: fn(m.weight.data) for name, m in model.named_modules() if isinstance(m, nn.Linear)}

@@ -39,6 +39,8 @@ GROUP_FACTOR = 4    # under row sharding, layers prepared together = GROUP_FACTO
 FACTOR_STREAMS = 16 # Hessian inverses in flight at a time on one GPU (each on its own CUDA stream)
 LOCAL_GROUP = 16    # one GPU: layers prepared together (Hessians, then their inverses side by side)
 TIMINGS = None      # set to a list to collect (phase, ms) CUDA-event pairs from the model walker
+TRACE = None        # set to a list: (group start, begin, end, K) events of every concurrent inverse
+HOST_LAPS = None    # set to a dict to add up host seconds per walker phase (launch-side cost)
 
 
 class _Prepared:
@@ -104,6 +106,10 @@ def gptq_quantize_model_weight(
     ready: Dict[str, _Prepared] = {}
     retiring: List[_Prepared] = []          # status flags not yet looked at (checked one group late)
     side_streams: List[torch.cuda.Stream] = []
+    # one pinned buffer for all status flags (a pinned allocation per layer would call
+    # cudaHostAlloc, which synchronises the device and serialises the concurrent inverses)
+    flags_host = torch.zeros(max(1, len(calibrated)), dtype=torch.int32).pin_memory() \
+        if torch.cuda.is_available() else None
 
     def retire():
         for p in retiring:
@@ -125,6 +131,9 @@ def gptq_quantize_model_weight(
             side_streams.append(torch.cuda.Stream(device))
         start = torch.cuda.Event()
         start.record(main)
+        if TRACE is not None:
+            trace_start = torch.cuda.Event(enable_timing=True)
+            trace_start.record(main)
         out, k = [], 0
         for name, H, owner in jobs:
             if H is None or n_streams <= 1 or (_dist.is_sharded() and _dist.rank() != owner):
@@ -135,8 +144,15 @@ def gptq_quantize_model_weight(
             if k <= n_streams:
                 side.wait_event(start)
             with torch.cuda.stream(side):
+                if TRACE is not None:
+                    b = torch.cuda.Event(enable_timing=True)
+                    b.record(side)
                 p = _factor_stage(name, H, actorder, owner)
-                p.info_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+                if TRACE is not None:
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record(side)
+                    TRACE.append((trace_start, b, e, H.shape[0]))
+                p.info_host = flags_host[position[name]:position[name] + 1]
                 p.info_host.copy_(p.info, non_blocking=True)
                 p.done = torch.cuda.Event()
                 p.done.record(side)
@@ -165,8 +181,14 @@ def gptq_quantize_model_weight(
         hessians = [_hessian_stage(input_feat[n], m.weight.shape[1], device, perp_damp, nsamples)
                     for n, m in group]
         t1 = _mark()
+        import time as _time
+        h0 = _time.perf_counter()
         retire()                      # the previous group's flags: long since on the host
+        h1 = _time.perf_counter()
         prepared = factor_concurrently([(n, H, owner[n]) for (n, _m), H in zip(group, hessians)], device)
+        if HOST_LAPS is not None:
+            HOST_LAPS["retire"] = HOST_LAPS.get("retire", 0.0) + (h1 - h0)
+            HOST_LAPS["factor launch"] = HOST_LAPS.get("factor launch", 0.0) + (_time.perf_counter() - h1)
         t2 = _mark()
         if world > 1:
             flags = []
@@ -217,14 +239,15 @@ def gptq_quantize_model_weight(
 
 def _factor_stream_count(K: int, n_jobs: int, device) -> int:
     """Factorisations in flight at once on this GPU: FACTOR_STREAMS, fewer when their workspaces
-    (3 K^2 floats + fp16 operand planes each, cached per stream) would not fit in half of the free
-    memory."""
+    (3 K^2 floats + fp16 operand planes each, cached per stream) and matrices would not fit in 60 %
+    of the memory that is free or sitting unused in torch's allocator cache."""
     if n_jobs <= 1 or K <= 0:
         return min(1, n_jobs)
     from b200q import _lib as _l
     per = _l.load().b200q_spd_inverse_workspace(K) + 3 * 4 * K * K
     free, _total = torch.cuda.mem_get_info(device)
-    return int(max(1, min(FACTOR_STREAMS, n_jobs, (free // 2) // max(per, 1))))
+    free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    return int(max(1, min(FACTOR_STREAMS, n_jobs, int(free * 0.6) // max(per, 1))))
 
 
 def _deal_layers(layers, world: int) -> Dict[str, int]:

@@ -59,20 +59,29 @@ def pseudo_quantize_tensor(w: Tensor, n_bit: int = 4, q_group_size: int = -1) ->
     return out if src == out.device else out.to(src)
 
 
+CALIB_ON_DEVICE = False   # True: get_calib_feat returns one CUDA [n_batches, C] matrix per Linear
+
+
 def get_calib_feat(model: nn.Module, tokenizer: Any, calib_samples: List[Tensor],
                    verbose: bool = True) -> Dict[str, List[Tensor]]:
     """Per-Linear list of mean|x| vectors, one per calibration batch (reference:
-    quantization_utils.py:204-262).  The reduction over tokens runs in b200q's act_meanabs kernel;
-    each vector is returned on the CPU as the reference does."""
+    quantization_utils.py:204-262).  The reduction over tokens runs in b200q's act_meanabs kernel.
+
+    The reference's hook moves every vector to the host as it is produced (`.cpu()`, :231): one
+    device synchronisation per Linear per batch.  Here the rows stay on the device while the
+    calibration batches run and each layer's [n_batches, C] matrix crosses
+    to the host ONCE at the end; the returned dict has the reference's layout (lists of CPU [C]
+    tensors in the activations' dtype).  With CALIB_ON_DEVICE = True nothing is copied back: the
+    values are CUDA [n_batches, C] matrices, which the AWQ / GPTQ walkers accept wherever they
+    accept the lists (a matrix iterates and sums row by row like the list)."""
     import tqdm
 
-    stats: Dict[str, List[Tensor]] = {}
+    rows: Dict[str, List[Tensor]] = {}
 
     def make_hook(name: str):
         def hook(_m, inputs, _out):
             x = inputs[0] if isinstance(inputs, tuple) else inputs
-            v = _ops.act_meanabs(_ops.to_device(x.detach())).to(x.dtype).cpu()
-            stats.setdefault(name, []).append(v)
+            rows.setdefault(name, []).append(_ops.act_meanabs(_ops.to_device(x.detach())).to(x.dtype))
         return hook
 
     handles = [m.register_forward_hook(make_hook(n)) for n, m in model.named_modules()
@@ -87,7 +96,9 @@ def get_calib_feat(model: nn.Module, tokenizer: Any, calib_samples: List[Tensor]
     finally:
         for h in handles:
             h.remove()
-    return stats
+    if CALIB_ON_DEVICE:
+        return {n: torch.stack(v) for n, v in rows.items()}
+    return {n: list(torch.stack(v).cpu().unbind(0)) for n, v in rows.items()}
 
 
 # ==================================================================================================

@@ -262,6 +262,22 @@ def test_get_calib_feat_and_collect_act_scales_hooks():
     torch.testing.assert_close(feats["0"][1], samples[1].reshape(-1, 64).abs().mean(0), rtol=1e-5, atol=1e-7)
     assert torch.equal(scales["0"], x0.abs().amax(0))
     assert scales["2"].shape == (128,)
+    # on-device capture: same numbers, no host copies, and the AWQ walker takes
+    # the [n_batches, C] matrices where it takes the reference's lists
+    import awq_quantizer as aq
+    qu.CALIB_ON_DEVICE = True
+    try:
+        dev_feats = qu.get_calib_feat(net, None, samples, verbose=False)
+    finally:
+        qu.CALIB_ON_DEVICE = False
+    assert dev_feats["0"].is_cuda and dev_feats["0"].shape == (3, 64)
+    assert torch.equal(dev_feats["0"].cpu(), torch.stack(feats["0"]))
+    a = nn.Sequential(nn.Linear(64, 128), nn.ReLU(), nn.Linear(128, 32)).cuda()
+    b = nn.Sequential(nn.Linear(64, 128), nn.ReLU(), nn.Linear(128, 32)).cuda()
+    b.load_state_dict(a.state_dict())
+    aq.awq_quantize_model_weight(a, 4, 32, feats, 0.05, 2.0)
+    aq.awq_quantize_model_weight(b, 4, 32, dev_feats, 0.05, 2.0)
+    assert torch.equal(a[0].weight.data, b[0].weight.data) and torch.equal(a[2].weight.data, b[2].weight.data)
 
 
 def test_importance_sum_is_pythons_left_to_right():

@@ -97,3 +97,62 @@ def test_export_model_file_round_trip_dequantizes_to_the_quantizer_output(tmp_pa
     for name, lin in (("0", net[0]), ("2", net[2])):
         want = pseudo_quantize_tensor(lin.weight.data.clone(), 4, 128)
         assert torch.equal(E.dequantize(loaded[name]).cpu(), want.cpu())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("b,G", [(4, 128), (3, 64), (4, -1)])
+def test_pot_export_round_trips_and_codes_are_the_oracles(dtype, b, G):
+    """POT exponent + sign plane.  dequantize(record) is pot_quantize_tensor's output
+    bit for bit, and the exponents are the oracle's (pot_apot_quantizer.py:104-107)."""
+    from b200q import export as E
+    from pot_apot_quantizer import pot_quantize_tensor
+    g = torch.Generator().manual_seed(b * 13 + 1)
+    W = (torch.randn(48, 512, generator=g) * 0.05).to(dtype)
+    W[3, 7] = 0.0                                       # sign(0) = 0: the extra "zero" symbol
+    W[10] = 0.0                                         # an all-zero group
+    rec = E.export_pot(W.cuda(), b, G)
+    assert rec["qweight"].shape == (48, 512 * b // 32) and "zero_mask" in rec
+    got = E.dequantize(rec)
+    assert torch.equal(got, pot_quantize_tensor(W.cuda(), b, G))
+    want = O.pot_quant(W, b, G)
+    assert torch.equal(got.cpu(), want["out"])
+    codes = E.unpack_codes(rec["qweight"], 512, b).cpu().to(torch.int32)
+    nz = want["out"] != 0
+    assert torch.equal((codes & ((1 << (b - 1)) - 1))[nz], want["exps"].reshape(48, 512).to(torch.int32)[nz])
+    assert torch.equal((codes >> (b - 1)).bool()[nz], (want["out"] < 0)[nz])
+    # without zeros no mask is stored
+    assert "zero_mask" not in E.export_pot((torch.rand(8, 128, generator=g) + 0.1).to(dtype).cuda(), b, G)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("b,k,G", [(4, 2, 128), (8, 2, 128), (2, 1, 64), (4, 2, -1)])
+def test_apot_export_round_trips_and_codes_are_the_oracles(dtype, b, k, G):
+    """APOT level-index plane (pot_apot_quantizer.py:294-298)."""
+    from b200q import export as E
+    from pot_apot_quantizer import apot_quantize_tensor
+    g = torch.Generator().manual_seed(b * 17 + k)
+    W = (torch.randn(40, 512, generator=g) * 0.05).to(dtype)
+    rec = E.export_apot(W.cuda(), b, G, k)
+    assert rec["levels"].numel() <= 32 and rec["bits"] <= 5
+    got = E.dequantize(rec)
+    assert torch.equal(got, apot_quantize_tensor(W.cuda(), b, G, k))
+    want = O.apot_quant(W, b, G, k)
+    assert torch.equal(got.cpu(), want["out"])
+    codes = E.unpack_codes(rec["qweight"], 512, rec["bits"]).cpu().to(torch.int32)
+    assert torch.equal(codes, want["level_idx"].reshape(40, 512).to(torch.int32))
+
+
+@pytest.mark.gpu
+def test_export_model_pot_apot_files(tmp_path):
+    import torch.nn as nn
+    from b200q import export as E
+    torch.manual_seed(5)
+    net = nn.Sequential(nn.Linear(256, 64, bias=False), nn.Linear(128, 32, bias=False))
+    for scheme in ("pot", "apot"):
+        recs = E.export_model(net, 4, 128, scheme)
+        E.save_records(tmp_path / f"{scheme}.pt", recs)
+        back = E.load_records(tmp_path / f"{scheme}.pt", device="cuda")
+        for name, rec in recs.items():
+            assert torch.equal(E.dequantize(back[name]), E.dequantize(rec))
