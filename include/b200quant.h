@@ -74,6 +74,19 @@ int b200q_pack_codes(const uint8_t* codes, int64_t N, int64_t K, int n_bit, uint
 int b200q_unpack_codes(const uint32_t* packed, int64_t N, int64_t K, int n_bit, uint8_t* codes,
                        void* stream);
 
+/* ---- W4A16 GEMM on a packed record -----------------------------
+ * Y[M, N] = X[M, K] * dequant(qweight)[N, K]^T: the nn.Linear forward of the reference's
+ * perplexity loop (ref: quantization_utils.py:269-322) evaluated on the PACKED weight the export
+ * produces -- 4-bit codes (eight per uint32, b200q_pack_codes layout), fp32 scale / zero point per
+ * group of `group` input channels ((q - zero) * scale, ref: quantization_utils.py:405).  The
+ * dequantisation runs inside the tcgen05 GEMM's operand pipeline; no fp16 copy of W is made.
+ *   X: 16-bit activations (act_dtype = B200Q_F16 / B200Q_BF16), row-major, K % 8 == 0
+ *   rec_dtype: dtype the weight was quantised in (its scale arithmetic is reproduced);
+ *   Y: act_dtype, or fp32 when out_f32 != 0. */
+int b200q_w4a16_gemm(const void* X, int64_t M, int64_t K, int act_dtype, const uint32_t* qweight,
+                     const float* scales, const float* zeros, int64_t N, int64_t group,
+                     int rec_dtype, void* Y, int out_f32, void* stream);
+
 /* ---- torch-CPU log2 semantics, exported for the CPU test-suite -------------------
  * rne(log2f(r)) and floor(log2f(m)) as torch's CPU kernel evaluates them are step
  * functions of r; the library tabulates the step positions on the host at load

@@ -49,6 +49,8 @@ SIGNATURES = {
     "b200q_packed_words_per_row": (c_i64, [c_i64, C.c_int]),
     "b200q_pack_codes": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp]),
     "b200q_unpack_codes": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp]),
+    "b200q_w4a16_gemm": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp, c_fp, c_fp, c_i64, c_i64, C.c_int,
+                                   c_vp, C.c_int, c_vp]),
     "b200q_selftest_div": (C.c_int, [c_i64, C.c_uint64, C.POINTER(c_i64), c_vp]),
     "b200q_topk_colmul": (C.c_int, [c_fp, c_i64, c_i64, C.c_float, c_fp, c_vp, c_vp]),
     "b200q_awq_layer": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp, c_i64, C.c_int,

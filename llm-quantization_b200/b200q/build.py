@@ -31,6 +31,7 @@ SOURCES = {
     "linalg.cu": [],
     "splitgemm.cu": [],
     "packing.cu": [],
+    "qgemm.cu": [],
 }
 
 
