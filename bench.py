@@ -672,6 +672,7 @@ def main():
         # ------------------------------------------------------------ end to end, host-resident weights
         e2e = None
         if not args.no_e2e:
+            reset(model, originals)          # drop the device-resident quantized copies first
             hm, flat, total = host_model()
             # per-batch statistics arrive on the host, as the reference's hooks produce them (.cpu())
             stats_host = {K: v.cpu() for K, v in stats_by_K.items()}

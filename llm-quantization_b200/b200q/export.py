@@ -159,9 +159,9 @@ def dequantize(record: Dict) -> torch.Tensor:
     elif record["scheme"] == "apot":
         G = record["group"]
         idx = codes.long().reshape(-1, G)
-        # scale (a value of the weight's dtype) times the fp32 level, one rounding, then the cast
-        # back to the weight's dtype (pot_apot_quantizer.py:335-340)
-        w = (record["scales"].reshape(-1, 1).float() * record["levels"].float()[idx]).to(dtype)
+        # the reference gathers the levels into a tensor of the WEIGHT's dtype (zeros_like(w), :326,
+        # :335) and multiplies by the scale there (:340): level rounded to dtype, product rounded
+        w = record["scales"].reshape(-1, 1).to(dtype) * record["levels"].to(dtype)[idx]
     else:
         raise ValueError(f"unknown scheme {record['scheme']!r}")
     return w.reshape(shape)

@@ -159,7 +159,11 @@ def _run_host_layers(items: List[Tuple[str, nn.Linear]], compute: Compute) -> No
                 new = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
                 new.copy_(out, non_blocking=True)
                 _assign(m, new)
-        pending.append(out)
+            copied = torch.cuda.Event()
+            copied.record(d2h)
+        pending.append((copied, out))
+        while pending and pending[0][0].query():      # results whose copy has finished can go
+            pending.pop(0)
     d2h.synchronize()
     cur.wait_stream(d2h)
     pending.clear()

@@ -67,7 +67,7 @@ class FactorizationError(_lib.B200QuantError):
 
 def spd_inverse(H: torch.Tensor, ridge: float = 0.0, want_inverse: bool = True,
                 want_upper: bool = False, owner: int = 0, broadcast: bool = True,
-                check: bool = True, return_info: bool = False):
+                check: bool = True, return_info: bool = False, buffers: Optional[dict] = None):
     """inv(H + ridge I) (and/or the upper Cholesky factor U of it, U^T U = inverse) for a CUDA
     fp32 SPD matrix.  Returns Hinv, U or (Hinv, U).  Under row sharding rank `owner` computes and
     the result is broadcast (the inverse is shared by all row shards); with broadcast=False the
@@ -78,17 +78,32 @@ def spd_inverse(H: torch.Tensor, ridge: float = 0.0, want_inverse: bool = True,
     check=True reads it (one host sync) and raises FactorizationError -- on every rank under
     sharding -- instead of handing back garbage; check=False leaves that to the caller, who gets
     the int32 flag tensor with return_info=True (the model walker checks a whole group of layers
-    with one sync)."""
+    with one sync).
+
+    buffers: optional {"out": [K,K] fp32, "scratch": [K,K] fp32, "info": int32[1]} preallocated by
+    the caller; nothing is then allocated here (the walker runs many inverses on side streams,
+    where allocator traffic would synchronise them)."""
     assert H.is_cuda and H.dtype == torch.float32 and H.dim() == 2 and H.shape[0] == H.shape[1]
     K = H.shape[0]
     lib = _lib.load()
-    Hinv = torch.empty_like(H) if want_inverse else None
-    U = torch.empty_like(H) if want_upper else None
-    info = torch.zeros(1, dtype=torch.int32, device=H.device)
+    buffers = buffers or {}
+    out = buffers.get("out")
+    Hinv = (out if out is not None else torch.empty_like(H)) if want_inverse else None
+    U = (out if (out is not None and not want_inverse) else torch.empty_like(H)) if want_upper else None
+    info = buffers.get("info")
+    if info is None:
+        info = torch.zeros(1, dtype=torch.int32, device=H.device)
+    else:
+        info.zero_()
     if not _dist.is_sharded() or _dist.rank() == owner:
         A = H.contiguous()
         if ridge != 0.0:
-            A = hessian_finalize(A.clone(), 1.0, ridge)
+            scratch = buffers.get("scratch")
+            if scratch is not None:
+                scratch.copy_(A)
+                A = hessian_finalize(scratch, 1.0, ridge)
+            else:
+                A = hessian_finalize(A.clone(), 1.0, ridge)
         with _on(H.device):
             work = _workspace(H.device, lib.b200q_spd_inverse_workspace(K))
             rc = lib.b200q_spd_inverse(A.data_ptr(), None if Hinv is None else Hinv.data_ptr(),
@@ -118,12 +133,13 @@ def raise_if_not_spd(info, K: int, what: str = "spd_inverse") -> None:
 
 
 def compensation_factor(H: torch.Tensor, perm: Optional[torch.Tensor] = None, owner: int = 0,
-                        broadcast: bool = True, check: bool = True, return_info: bool = False):
+                        broadcast: bool = True, check: bool = True, return_info: bool = False,
+                        buffers: Optional[dict] = None):
     """U = chol(inv(H_perm + 1e-6 I), upper): what the compensated column loop multiplies by."""
     if perm is not None:
         H = H[perm][:, perm]
     return spd_inverse(H.contiguous(), ridge=1e-6, want_inverse=False, want_upper=True, owner=owner,
-                       broadcast=broadcast, check=check, return_info=return_info)
+                       broadcast=broadcast, check=check, return_info=return_info, buffers=buffers)
 
 
 def gptq_compensated(W: torch.Tensor, H: Optional[torch.Tensor], n_bit: int, group: int,

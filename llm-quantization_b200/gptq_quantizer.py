@@ -110,6 +110,19 @@ def gptq_quantize_model_weight(
     # cudaHostAlloc, which synchronises the device and serialises the concurrent inverses)
     flags_host = torch.zeros(max(1, len(calibrated)), dtype=torch.int32).pin_memory() \
         if torch.cuda.is_available() else None
+    # per-slot matrices of the concurrent inverses (slot = position inside a group): allocated on
+    # the main stream once per size and reused by every group, so that the side streams never touch
+    # the allocator (a cudaMalloc / cudaFree there synchronises the device and serialises them)
+    slots: Dict[int, dict] = {}
+
+    def slot_buffers(k, K, device):
+        b = slots.get(k)
+        if b is None or b["out"].shape[0] != K:
+            b = {"out": torch.empty((K, K), dtype=torch.float32, device=device),
+                 "scratch": torch.empty((K, K), dtype=torch.float32, device=device),
+                 "info": torch.zeros(1, dtype=torch.int32, device=device)}
+            slots[k] = b
+        return b
 
     def retire():
         for p in retiring:
@@ -129,11 +142,14 @@ def gptq_quantize_model_weight(
         n_streams = _factor_stream_count(max((j[1].shape[0] for j in mine), default=0), len(mine), device)
         while len(side_streams) < n_streams:
             side_streams.append(torch.cuda.Stream(device))
-        start = torch.cuda.Event()
-        start.record(main)
         if TRACE is not None:
             trace_start = torch.cuda.Event(enable_timing=True)
             trace_start.record(main)
+        # (slot buffers first, on the main stream, before anything is queued on the side streams)
+        bufs = {j[0]: slot_buffers(i, j[1].shape[0], device) for i, j in enumerate(mine)} \
+            if n_streams > 1 else {}
+        start = torch.cuda.Event()
+        start.record(main)
         out, k = [], 0
         for name, H, owner in jobs:
             if H is None or n_streams <= 1 or (_dist.is_sharded() and _dist.rank() != owner):
@@ -147,7 +163,7 @@ def gptq_quantize_model_weight(
                 if TRACE is not None:
                     b = torch.cuda.Event(enable_timing=True)
                     b.record(side)
-                p = _factor_stage(name, H, actorder, owner)
+                p = _factor_stage(name, H, actorder, owner, bufs[name])
                 if TRACE is not None:
                     e = torch.cuda.Event(enable_timing=True)
                     e.record(side)
@@ -156,12 +172,11 @@ def gptq_quantize_model_weight(
                 p.info_host.copy_(p.info, non_blocking=True)
                 p.done = torch.cuda.Event()
                 p.done.record(side)
-            # memory handed across streams: H is read by the side stream, the factor (allocated
-            # there) by the main stream
+            # memory handed across streams: H is read by the side stream (the factor and the flag
+            # live in slot buffers owned by the main stream; the main stream waits for `done`)
             H.record_stream(side)
-            for t in (p.factor, p.perm, p.info):
-                if t is not None:
-                    t.record_stream(main)
+            if p.perm is not None:
+                p.perm.record_stream(main)
             out.append(p)
         for p in out:
             if p.done is not None:
@@ -239,7 +254,7 @@ def gptq_quantize_model_weight(
 
 def _factor_stream_count(K: int, n_jobs: int, device) -> int:
     """Factorisations in flight at once on this GPU: FACTOR_STREAMS, fewer when their workspaces
-    (3 K^2 floats + fp16 operand planes each, cached per stream) and matrices would not fit in 60 %
+    (3 K^2 floats + fp16 operand planes each, cached per stream) and matrices would not fit in 40 %
     of the memory that is free or sitting unused in torch's allocator cache."""
     if n_jobs <= 1 or K <= 0:
         return min(1, n_jobs)
@@ -247,7 +262,7 @@ def _factor_stream_count(K: int, n_jobs: int, device) -> int:
     per = _l.load().b200q_spd_inverse_workspace(K) + 3 * 4 * K * K
     free, _total = torch.cuda.mem_get_info(device)
     free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
-    return int(max(1, min(FACTOR_STREAMS, n_jobs, int(free * 0.6) // max(per, 1))))
+    return int(max(1, min(FACTOR_STREAMS, n_jobs, int(free * 0.4) // max(per, 1))))
 
 
 def _deal_layers(layers, world: int) -> Dict[str, int]:
@@ -352,7 +367,7 @@ def _hessian_stage(input_feat, K: int, device, perp_damp: float, nsamples: int):
     return gptq_hessian(input_feat, K, device, perp_damp, nsamples)
 
 
-def _factor_stage(name: str, H, actorder: bool, owner: int = 0) -> _Prepared:
+def _factor_stage(name: str, H, actorder: bool, owner: int = 0, buffers=None) -> _Prepared:
     """The act-order permutation (compensated mode only) and what the column stage needs from the
     inverse -- H^-1 in parity mode (built like the reference builds it; its output does not depend
     on it), U = chol(H^-1) in compensated mode -- launched on the CURRENT stream, status flag left
@@ -365,10 +380,10 @@ def _factor_stage(name: str, H, actorder: bool, owner: int = 0) -> _Prepared:
     if MODE == "compensated":
         perm = torch.argsort(torch.diag(H), descending=True) if actorder else None
         U, info = _tops.compensation_factor(H, perm, owner=owner, broadcast=False, check=False,
-                                            return_info=True)
+                                            return_info=True, buffers=buffers)
         return _Prepared(name, H, perm, U, K, info=info)
     Hinv, info = _tops.spd_inverse(H, ridge=1e-6, owner=owner, broadcast=False, check=False,
-                                   return_info=True)
+                                   return_info=True, buffers=buffers)
     return _Prepared(name, H, None, Hinv, K, info=info)
 
 
