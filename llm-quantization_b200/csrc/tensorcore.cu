@@ -401,6 +401,238 @@ hessian_gemm_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
 }
 
 // =================================================================================================
+// 3b. the same product on CTA PAIRS (cta_group::2)
+// =================================================================================================
+// Two CTAs of a cluster (one TPC) compute one 256 x 256 output tile: the leader issues
+// tcgen05.mma.cta_group::2 with M = 256, each CTA stages ITS 128 rows of A and ITS 128 of the 256
+// columns of B (32 KiB per stage instead of 48) and ends up with its 128 x 256 slice of the
+// accumulator in its own TMEM.  Per flop that is half the shared-memory operand traffic and a
+// third less L2 -> SM traffic than the one-CTA kernel -- what matters here, because the step runs
+// at the 1 kW power limit and every byte not moved is clock.  Six stages fit.  Everything else
+// (SYRK tile skipping, band rasterisation, chunked accumulation with the running total in TMEM
+// columns [256, 512), per-sample weights, mirror-writing epilogue) is as in hessian_gemm_kernel.
+namespace hg2 {
+constexpr int BM = 256;          // output rows per CTA pair (128 per CTA)
+constexpr int BN = 256;          // output cols per CTA pair (each CTA stages 128 of them)
+constexpr int BKT = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 6;
+constexpr int BOX_CH = 64;
+constexpr int BOX_BYTES = BKT * BOX_CH * 2;                 // 8 KiB
+constexpr int A_BYTES = 2 * BOX_BYTES;                      // this CTA's 128 channels of A
+constexpr int B_BYTES = 2 * BOX_BYTES;                      // this CTA's 128 channels of B
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;              // 32 KiB per CTA
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int THREADS = 256;
+constexpr int RASTER_M = 8;      // 256-row tile rows per rasterisation band
+}  // namespace hg2
+
+template <bool BF16, bool PER_SAMPLE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(hg2::THREADS, 1)
+hessian_gemm2_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ partial,
+                     int64_t K, int64_t T, int64_t tokens_per_split, int tiles_n,
+                     const float* __restrict__ norms, int kb_per_sample) {
+  using namespace hg2;
+  constexpr uint32_t kTmemCols = PER_SAMPLE ? 512u : 256u;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);   // used in the leader
+  uint64_t* empty_bar = full_bar + STAGES;             // one per CTA, fed by the multicast commit
+  uint64_t* tmem_full_bar = empty_bar + STAGES;        // one per CTA, fed by the multicast commit
+  uint64_t* chunk_free_bar = tmem_full_bar + 1;        // leader: 8 epilogue warps (4 per CTA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(chunk_free_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int tile = blockIdx.x >> 1;
+  const int tiles_m = (int)((K + BM - 1) / BM);
+  const int band = tile / (RASTER_M * tiles_n);
+  const int within = tile % (RASTER_M * tiles_n);
+  const int band_rows = min(RASTER_M, tiles_m - band * RASTER_M);
+  const int n_blk = within / band_rows;
+  const int m_blk = band * RASTER_M + within % band_rows;
+  const int z = blockIdx.y;
+  // tiles entirely below the diagonal do not run (both CTAs of the pair take the same decision)
+  if (n_blk < m_blk) return;
+  const int64_t t0 = (int64_t)z * tokens_per_split;
+  const int64_t t1 = min(T, t0 + tokens_per_split);
+  const int num_kb = (int)((t1 - t0 + BKT - 1) / BKT);
+  const int chunk_kb = PER_SAMPLE ? kb_per_sample : max(num_kb, 1);
+  const int num_chunks = (num_kb + chunk_kb - 1) / chunk_kb;
+  const int sample0 = PER_SAMPLE ? (int)(t0 / ((int64_t)kb_per_sample * BKT)) : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(chunk_free_bar, 8);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair<kTmemCols>(tmem_slot);
+  tc_fence_before_sync();
+  cluster_sync_all();              // both CTAs' barriers and TMEM are ready before anyone signals
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs; completion is signalled on the LEADER's full barrier) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+        const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+        uint8_t* a_dst = smem + stage * STAGE_BYTES;
+        uint8_t* b_dst = a_dst + A_BYTES;
+        const int32_t tok = (int32_t)(t0 + (int64_t)kb * BKT);
+        const int32_t a_ch = m_blk * BM + (int)rank * 128;
+        const int32_t b_ch = n_blk * BN + (int)rank * 128;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          tma_load_2d_pair(a_dst + j * BOX_BYTES, &tmap, full_leader, a_ch + j * BOX_CH, tok);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          tma_load_2d_pair(b_dst + j * BOX_BYTES, &tmap, full_leader, b_ch + j * BOX_CH, tok);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: the leader's one thread drives both SMs' tensor cores =====
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN, BF16, /*a_mn=*/true, /*b_mn=*/true);
+      int stage = 0;
+      uint32_t phase = 0;
+      int kb = 0;
+      for (int ch = 0; ch < num_chunks; ++ch) {
+        if (PER_SAMPLE && ch > 0) {                  // both CTAs have folded the previous chunk in
+          mbar_wait(chunk_free_bar, (uint32_t)((ch - 1) & 1));
+          tc_fence_after_sync();
+        }
+        const int kb_end = min(num_kb, kb + chunk_kb);
+        for (bool first = true; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BKT / UMMA_K; ++k) {
+            const uint32_t koff = k * UMMA_K * 128;
+            const uint64_t da = make_smem_desc_sw128(a_addr + koff, BOX_BYTES, 1024);
+            const uint64_t db = make_smem_desc_sw128(b_addr + koff, BOX_BYTES, 1024);
+            mma_f16_ss_pair(tmem_base, da, db, idesc, (first && k == 0) ? 0u : 1u);
+          }
+          first = false;
+          mma_commit_pair(&empty_bar[stage]);     // frees the stage in BOTH CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        mma_commit_pair(tmem_full_bar);           // (chunk) accumulator complete, both CTAs
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: this CTA's 128 rows x 256 columns =====
+    const int q = warp & 3;
+    float* dst_base = partial + (int64_t)z * K * K;
+    const int64_t row0 = (int64_t)m_blk * BM + (int64_t)rank * 128;
+    const int64_t row = row0 + q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t free_leader = mapa_u32(smem_u32(chunk_free_bar), 0);
+    auto sample_weight = [&](int ch) {
+      if (norms == nullptr) return 1.f;
+      const float a = 1.f / (norms[sample0 + ch] + 1e-5f);     // gptq_quantizer.py:143
+      return a * a;
+    };
+    if (PER_SAMPLE) {
+      for (int ch = 0; ch + 1 < num_chunks; ++ch) {
+        mbar_wait(tmem_full_bar, (uint32_t)(ch & 1));
+        tc_fence_after_sync();
+        const float wgt = sample_weight(ch);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32], t[32];
+          tmem_ld_32x32(lane_base + (uint32_t)(c * 32), v);
+          if (ch > 0) {
+            tmem_ld_32x32(lane_base + (uint32_t)(BN + c * 32), t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = __float_as_uint(fmaf(wgt, __uint_as_float(v[j]), __uint_as_float(t[j])));
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(wgt * __uint_as_float(v[j]));
+          }
+          tmem_st_32x32(lane_base + (uint32_t)(BN + c * 32), v);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(free_leader);
+      }
+    }
+    if (num_chunks > 0) {
+      mbar_wait(tmem_full_bar, (uint32_t)((num_chunks - 1) & 1));
+      tc_fence_after_sync();
+    }
+    const float last_wgt = (PER_SAMPLE && num_chunks > 0) ? sample_weight(num_chunks - 1) : 1.f;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      if (num_chunks > 0) {
+        tmem_ld_32x32(lane_base + (uint32_t)(c * 32), v);
+        if (PER_SAMPLE) {
+          if (num_chunks > 1) {
+            uint32_t t[32];
+            tmem_ld_32x32(lane_base + (uint32_t)(BN + c * 32), t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = __float_as_uint(fmaf(last_wgt, __uint_as_float(v[j]), __uint_as_float(t[j])));
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(last_wgt * __uint_as_float(v[j]));
+          }
+        } else {
+          tmem_ld_wait();
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      const int64_t col0 = (int64_t)n_blk * BN + c * 32;
+      const int64_t warp_row0 = row0 + q * 32;
+      if (col0 + 32 <= warp_row0) continue;       // nothing of the upper triangle in this chunk
+      if (row < K) {
+        float* dst = dst_base + row * K + col0;
+        if (col0 >= row && col0 + 32 <= K) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j >= row && col0 + j < K) dst[j] = __uint_as_float(v[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int64_t col = col0 + j;
+        if (col > row && col < K && row < K) dst_base[col * K + row] = __uint_as_float(v[j]);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();              // the peer may still be reading its TMEM / using our barriers
+  if (warp == 2) tmem_dealloc_pair<kTmemCols>(tmem_base);
+}
+
+// =================================================================================================
 // 4. split reduction and finalisation
 // =================================================================================================
 __global__ void hessian_reduce_kernel(const float* __restrict__ partial, int splits, int64_t KK,
@@ -474,12 +706,24 @@ static int make_tmap_2d_16bit(CUtensorMap* map, const void* base, int64_t rows, 
 // the partial matrices.  `straight` = the single-split result can go to H directly (no such pass).
 // Constants are measured B200 figures (0.44 us per 128x256x64 stage under the sustained power
 // limit, ~6.5 us for 148 concurrent tile epilogues, 6.2 TB/s for the reduction).
+// CTA pairs (cta_group::2, hessian_gemm2_kernel) unless B200Q_HESSIAN_PAIR=0 (read once)
+static bool hessian_pair() {
+  static const bool on = []() {
+    const char* e = std::getenv("B200Q_HESSIAN_PAIR");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+
 static int hessian_splits(int64_t K, int64_t T, bool straight) {
-  const int64_t tm = (K + hg::BM - 1) / hg::BM, tn = (K + hg::BN - 1) / hg::BN;
+  const bool pair = hessian_pair();
+  const int64_t bm = pair ? hg2::BM : hg::BM;
+  const int64_t tm = (K + bm - 1) / bm, tn = (K + hg::BN - 1) / hg::BN;
   int64_t tiles = 0;                       // only tiles that touch the upper triangle run
   for (int64_t m = 0; m < tm; ++m)
     for (int64_t n = 0; n < tn; ++n)
-      if ((n + 1) * hg::BN > m * hg::BM) ++tiles;
+      if ((n + 1) * hg::BN > m * bm) ++tiles;
+  if (pair) tiles *= 2;                    // two SMs per tile
   const int64_t kblocks = (T + hg::BKT - 1) / hg::BKT;
   const int64_t max_s = std::max<int64_t>(1, std::min<int64_t>(16, kblocks / 8));
   int64_t best = 1;
@@ -876,16 +1120,30 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
   int rc = make_tmap_2d_16bit(&tmap, in_place ? X : static_cast<const void*>(w.Xs), T, K, hg::BKT,
                               hg::BOX_CH, bf16_ops);
   if (rc != B200Q_OK) return rc;
-  // (per-device attribute: the calls are cheap and idempotent)
-  if (cudaFuncSetAttribute(hessian_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           hg::SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(hessian_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           hg::SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(hessian_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           hg::SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(hessian_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           hg::SMEM_BYTES) != cudaSuccess)
-    return fail(B200Q_ECUDA, "hessian_gemm: cannot raise shared memory");
+  // (per-device attribute, set once per device and process)
+  {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && !done[dev]) {
+      bool ok = true;
+#define B200Q_HG_ATTR(KERNEL, BYTES) \
+      ok = ok && cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES) == cudaSuccess
+      B200Q_HG_ATTR((hessian_gemm_kernel<false, false>), hg::SMEM_BYTES);
+      B200Q_HG_ATTR((hessian_gemm_kernel<true, false>), hg::SMEM_BYTES);
+      B200Q_HG_ATTR((hessian_gemm_kernel<false, true>), hg::SMEM_BYTES);
+      B200Q_HG_ATTR((hessian_gemm_kernel<true, true>), hg::SMEM_BYTES);
+      B200Q_HG_ATTR((hessian_gemm2_kernel<false, false>), hg2::SMEM_BYTES);
+      B200Q_HG_ATTR((hessian_gemm2_kernel<true, false>), hg2::SMEM_BYTES);
+      B200Q_HG_ATTR((hessian_gemm2_kernel<false, true>), hg2::SMEM_BYTES);
+      B200Q_HG_ATTR((hessian_gemm2_kernel<true, true>), hg2::SMEM_BYTES);
+#undef B200Q_HG_ATTR
+      if (!ok) return fail(B200Q_ECUDA, "hessian_gemm: cannot raise shared memory");
+      done[dev] = true;
+    }
+  }
   const int64_t kblocks = (T + hg::BKT - 1) / hg::BKT;
   int splits = w.splits;
   int64_t tokens_per_split;
@@ -908,13 +1166,21 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
   float* gemm_out = straight ? H : w.partial;
   {
     KernelScope scope("hessian_gemm", 0, flops, st);
+    const bool pair = hessian_pair();
     const int tiles_n = (int)((K + hg::BN - 1) / hg::BN);
-    const int tiles_m = (int)((K + hg::BM - 1) / hg::BM);
-    dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)splits);
+    const int tiles_m = (int)((K + (pair ? hg2::BM : hg::BM) - 1) / (pair ? hg2::BM : hg::BM));
+    // pairs: two CTAs (one cluster) per 256 x 256 tile
+    dim3 grid((unsigned)(tiles_m * tiles_n * (pair ? 2 : 1)), (unsigned)splits);
     const float* norms = per_sample ? w.stats + n_samples : nullptr;
 #define B200Q_HG_LAUNCH(BF, PS)                                                                   \
-    hessian_gemm_kernel<BF, PS><<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(                        \
-        tmap, gemm_out, K, T, tokens_per_split, tiles_n, norms, kb_per_sample)
+    do {                                                                                          \
+      if (pair)                                                                                   \
+        hessian_gemm2_kernel<BF, PS><<<grid, hg2::THREADS, hg2::SMEM_BYTES, st>>>(                 \
+            tmap, gemm_out, K, T, tokens_per_split, tiles_n, norms, kb_per_sample);               \
+      else                                                                                        \
+        hessian_gemm_kernel<BF, PS><<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(                    \
+            tmap, gemm_out, K, T, tokens_per_split, tiles_n, norms, kb_per_sample);               \
+    } while (0)
     // (B200Q_HESSIAN_CHUNKED=0 keeps one long accumulation for A/B timing; per-sample always chunks)
     static const bool chunk_env = []() {
       const char* e = std::getenv("B200Q_HESSIAN_CHUNKED");
