@@ -471,7 +471,11 @@ def main():
     globals()["W_BIT"] = args.bits
     # the contract is ONE JSON line on stdout: progress text of the entry points (the reference's
     # functions print, e.g. "Searching for optimal scale factor...") goes to stderr
-    out = sys.stdout
+    # (NCCL and other native libraries write to file descriptor 1 directly: keep a private copy of
+    # it for the JSON line and point fd 1 at stderr)
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     sys.stdout = sys.stderr
 
     rank = int(os.environ.get("RANK", 0))

@@ -262,6 +262,26 @@ int64_t b200q_awq_search_workspace(int64_t N, int64_t K, int n_cand);
 int b200q_awq_search_loss(const void* W, int64_t N, int64_t K, int64_t group, int n_bit,
                           const uint8_t* salient, const float* sf_host, int n_cand, const float* H,
                           int dtype, void* work, float* loss, void* stream);
+/* same, with the folded operand Hb[n][k] = bf16(H[n][k] + H[k][n]) (k < n), bf16(H[n][n]) on the
+ * diagonal, 0 above it, supplied by the caller as a [K,K] bf16 matrix (multi-GPU runs build it from
+ * the packed exchange below and skip the fold pass). */
+int b200q_awq_search_loss_folded(const void* W, int64_t N, int64_t K, int64_t group, int n_bit,
+                                 const uint8_t* salient, const float* sf_host, int n_cand,
+                                 const void* Hb_folded, int dtype, void* work, float* loss,
+                                 void* stream);
+
+/* ---- symmetric [K,K] matrices between GPUs: the packed lower triangle (new) -----
+ * X^T X partial sums (ref: gptq_quantizer.py:144 accumulated over calibration samples dealt to
+ * the ranks) are exactly symmetric, so they are exchanged as row n = columns 0..n at offset
+ * n(n+1)/2: half the bytes of the square.  sym_fold_packed_bf16 turns packed elements [e0, e1)
+ * (a rank's reduce-scattered slice, P_slice pointing at element e0; elements past the triangle's
+ * end are padding and give 0) into the bf16 folded values of the AWQ search operand. */
+int64_t b200q_sym_packed_len(int64_t K);
+int b200q_sym_pack_lower(const float* H, int64_t K, float* P, void* stream);
+int b200q_sym_unpack_lower(const float* P, int64_t K, float* H, void* stream);
+int b200q_sym_fold_packed_bf16(const float* P_slice, int64_t K, int64_t e0, int64_t e1, void* out_bf16,
+                               void* stream);
+int b200q_sym_unpack_folded_bf16(const void* Pb, int64_t K, void* Hb, void* stream);
 
 #ifdef __cplusplus
 }

@@ -134,7 +134,7 @@ def awq_search_scale_factor(
     def start_gram(i, device):
         n, m = items[i]
         if supported(m.weight.shape[1]):
-            grams[n] = _tops.gram_matrix_begin(input_feat[n], m.weight.shape[1], device)
+            grams[n] = _tops.gram_matrix_begin(input_feat[n], m.weight.shape[1], device, want_folded=True)
 
     skipped = []
 

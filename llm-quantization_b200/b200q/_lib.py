@@ -65,6 +65,14 @@ SIGNATURES = {
     "b200q_awq_search_loss": (C.c_int, [c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp,
                                         C.POINTER(C.c_float), C.c_int, c_fp, C.c_int, c_vp, c_fp,
                                         c_vp]),
+    "b200q_awq_search_loss_folded": (C.c_int, [c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp,
+                                               C.POINTER(C.c_float), C.c_int, c_vp, C.c_int, c_vp, c_fp,
+                                               c_vp]),
+    "b200q_sym_packed_len": (c_i64, [c_i64]),
+    "b200q_sym_pack_lower": (C.c_int, [c_fp, c_i64, c_fp, c_vp]),
+    "b200q_sym_unpack_lower": (C.c_int, [c_fp, c_i64, c_fp, c_vp]),
+    "b200q_sym_fold_packed_bf16": (C.c_int, [c_fp, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "b200q_sym_unpack_folded_bf16": (C.c_int, [c_vp, c_i64, c_vp, c_vp]),
     "b200q_hessian_finalize": (C.c_int, [c_fp, c_i64, C.c_float, C.c_float, c_vp]),
     "b200q_spd_inverse_workspace": (c_i64, [c_i64]),
     "b200q_spd_inverse": (C.c_int, [c_fp, c_fp, c_fp, c_i64, c_vp, c_vp, c_vp]),

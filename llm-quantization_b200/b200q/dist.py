@@ -112,6 +112,44 @@ def allreduce_sum_async(t: torch.Tensor):
     return None
 
 
+def backend_is_nccl() -> bool:
+    return is_sharded() and td.get_backend(_active_group) == "nccl"
+
+
+def reduce_scatter_sum(out: torch.Tensor, inp: torch.Tensor) -> torch.Tensor:
+    """out (this rank's 1/world slice) = sum over ranks of the matching slice of inp."""
+    with _Timed(inp):
+        td.reduce_scatter_tensor(out, inp, op=td.ReduceOp.SUM, group=_active_group)
+    return out
+
+
+def all_gather_into(out: torch.Tensor, inp: torch.Tensor) -> torch.Tensor:
+    with _Timed(out):
+        td.all_gather_into_tensor(out, inp, group=_active_group)
+    return out
+
+
+class timed_wait:
+    """Brackets a wait of the CURRENT stream on communication work (an event of the communication
+    stream) the way the collectives above are bracketed, so that bench.py's nccl_exposed counts it."""
+
+    def __init__(self, nbytes: int = 0):
+        self.nbytes, self.e0 = nbytes, None
+
+    def __enter__(self):
+        if WAIT_EVENTS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None and WAIT_EVENTS is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            WAIT_EVENTS.append((self.e0, e1, self.nbytes))
+        return False
+
+
 def broadcast(t: torch.Tensor, src: int = 0) -> torch.Tensor:
     if is_sharded():
         with _Timed(t):

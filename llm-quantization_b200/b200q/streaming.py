@@ -59,7 +59,8 @@ class ActivationStream:
         K = self.in_features
         H = self.H.clone() if self.H is not None else \
             torch.zeros((K, K), dtype=torch.float32, device=torch.device(device))
-        return _dist.allreduce_sum(H)
+        from . import tensor_ops as _tops
+        return _tops.allreduce_symmetric(H)
 
     def total_rows(self, device) -> int:
         if not _dist.is_sharded():

@@ -170,18 +170,112 @@ def gptq_compensated(W: torch.Tensor, H: Optional[torch.Tensor], n_bit: int, gro
     return Q.to(W.dtype)
 
 
+# ---- symmetric matrices between GPUs: the packed lower triangle ---------------------------------
+PACKED_EXCHANGE = True     # False: plain fp32 [K,K] all-reduce (A/B timing, non-NCCL backends)
+_comm_streams = {}
+
+
+def _comm_stream(device) -> torch.cuda.Stream:
+    s = _comm_streams.get(device.index)
+    if s is None:
+        s = _comm_streams[device.index] = torch.cuda.Stream(device)
+    return s
+
+
+def sym_pack_lower(H: torch.Tensor, pad_to: int = 1) -> torch.Tensor:
+    """fp32 [K,K] symmetric -> its lower triangle as a vector (row n = columns 0..n at offset
+    n(n+1)/2), length rounded up to a multiple of pad_to (padding uninitialised)."""
+    K = H.shape[0]
+    L = K * (K + 1) // 2
+    P = torch.empty((L + pad_to - 1) // pad_to * pad_to, dtype=torch.float32, device=H.device)
+    with _on(H.device):
+        rc = _lib.load().b200q_sym_pack_lower(H.data_ptr(), K, P.data_ptr(), _stream())
+    _lib.check(rc, "sym_pack_lower")
+    return P
+
+
+def sym_unpack_lower(P: torch.Tensor, K: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """the packed triangle back into a full symmetric fp32 [K,K]."""
+    H = out if out is not None else torch.empty((K, K), dtype=torch.float32, device=P.device)
+    with _on(P.device):
+        rc = _lib.load().b200q_sym_unpack_lower(P.data_ptr(), K, H.data_ptr(), _stream())
+    _lib.check(rc, "sym_unpack_lower")
+    return H
+
+
+def allreduce_symmetric(H: torch.Tensor) -> torch.Tensor:
+    """In-place sum over the ranks of a SYMMETRIC fp32 [K,K] matrix; only the lower triangle
+    travels (half the bytes of all-reducing the square)."""
+    if not _dist.is_sharded():
+        return H
+    if not (PACKED_EXCHANGE and H.is_cuda):
+        return _dist.allreduce_sum(H)
+    P = sym_pack_lower(H)
+    _dist.allreduce_sum(P)
+    return sym_unpack_lower(P, H.shape[0], out=H)
+
+
+class FoldedGram:
+    """The AWQ search operand already folded onto its lower triangle: bf16 [K,K],
+    Hb[n][k] = H[n][k] + H[k][n] for k < n, H[n][n] on the diagonal, 0 above."""
+    __slots__ = ("Hb",)
+
+    def __init__(self, Hb):
+        self.Hb = Hb
+
+
 class PendingGram:
     """A Gram matrix whose cross-rank sum may still be in flight (see gram_matrix_begin)."""
-    __slots__ = ("H", "work", "rows_total")
+    __slots__ = ("H", "work", "rows_total", "folded", "event", "nbytes")
 
-    def __init__(self, H, work, rows_total):
+    def __init__(self, H, work, rows_total, folded=None, event=None, nbytes=0):
         self.H, self.work, self.rows_total = H, work, rows_total
+        self.folded, self.event, self.nbytes = folded, event, nbytes
 
 
-def gram_matrix_begin(input_feat: Sequence, in_features: int, device) -> PendingGram:
+def _exchange_folded(H: torch.Tensor) -> PendingGram:
+    """Partial X^T X of this rank -> the search operand summed over all ranks, with the exchange on
+    the communication stream:  pack lower triangle (fp32) -> reduce-scatter -> every rank folds ITS
+    slice to bf16 -> all-gather (bf16) -> unpack into the [K,K] operand.  Per rank that moves
+    (w-1)/w * 3 K^2 bytes against 8 K^2 for the fp32 all-reduce of the square, and the fold pass is
+    shared out over the ranks."""
+    K = H.shape[0]
+    dev = H.device
+    w, r = _dist.world_size(), _dist.rank()
+    lib = _lib.load()
+    main = torch.cuda.current_stream(dev)
+    comm = _comm_stream(dev)
+    P = sym_pack_lower(H, pad_to=8 * w)
+    Lp = P.numel()
+    per = Lp // w
+    comm.wait_stream(main)
+    with torch.cuda.stream(comm):
+        mine = torch.empty(per, dtype=torch.float32, device=dev)
+        _dist.reduce_scatter_sum(mine, P)
+        mine16 = torch.empty(per, dtype=torch.bfloat16, device=dev)
+        rc = lib.b200q_sym_fold_packed_bf16(mine.data_ptr(), K, r * per, (r + 1) * per,
+                                            mine16.data_ptr(), _stream())
+        _lib.check(rc, "sym_fold_packed_bf16")
+        Pb = torch.empty(Lp, dtype=torch.bfloat16, device=dev)
+        _dist.all_gather_into(Pb, mine16)
+        Hb = torch.empty((K, K), dtype=torch.bfloat16, device=dev)
+        rc = lib.b200q_sym_unpack_folded_bf16(Pb.data_ptr(), K, Hb.data_ptr(), _stream())
+        _lib.check(rc, "sym_unpack_folded_bf16")
+        ev = torch.cuda.Event()
+        ev.record(comm)
+    P.record_stream(comm)
+    Hb.record_stream(main)
+    return PendingGram(None, None, 0, folded=FoldedGram(Hb), event=ev, nbytes=Lp * 4 + Lp * 2)
+
+
+def gram_matrix_begin(input_feat: Sequence, in_features: int, device,
+                      want_folded: bool = False) -> PendingGram:
     """Launch X^T X over this rank's share of the calibration rows and, under row sharding, START
     the all-reduce of the partial sums without waiting for it: the caller can queue the next
-    layer's kernels behind this one and pick the result up later with gram_matrix_end."""
+    layer's kernels behind this one and pick the result up later with gram_matrix_end.
+    want_folded: the caller is the AWQ search, which only needs the matrix folded onto its lower
+    triangle in bf16 -- under sharding the exchange then runs packed (see _exchange_folded) and
+    gram_matrix_end returns a FoldedGram."""
     device = torch.device(device)
     K = in_features
     from .streaming import ActivationStream
@@ -209,6 +303,10 @@ def gram_matrix_begin(input_feat: Sequence, in_features: int, device) -> Pending
         lo, hi = _dist.shard_rows(n, _dist.world_size(), _dist.rank())
         H = hessian_accum(X[lo * rows:hi * rows], rows, normalize=False) if hi > lo else \
             torch.zeros((K, K), dtype=torch.float32, device=device)
+        if want_folded and PACKED_EXCHANGE and _dist.backend_is_nccl():
+            p = _exchange_folded(H)
+            p.rows_total = rows_total
+            return p
         work = _dist.allreduce_sum_async(H)
     else:
         H = hessian_accum(X, rows, normalize=False)
@@ -218,6 +316,11 @@ def gram_matrix_begin(input_feat: Sequence, in_features: int, device) -> Pending
 def gram_matrix_end(p: PendingGram, normalise: bool = True) -> torch.Tensor:
     """The finished matrix: X^T X / rows, or the plain sum X^T X with normalise=False (a caller
     whose result is linear in H can apply 1 / p.rows_total to its own, much smaller, output)."""
+    if p.folded is not None:
+        assert not normalise, "a folded Gram matrix comes as the plain sum"
+        with _dist.timed_wait(p.nbytes):
+            torch.cuda.current_stream(p.folded.Hb.device).wait_event(p.event)
+        return p.folded
     if p.work is not None:
         p.work.wait()                       # orders the current stream after the all-reduce
         p.work = None
@@ -235,7 +338,9 @@ def awq_search_losses(W: torch.Tensor, H: torch.Tensor, salient_mask: torch.Tens
                       group: int, candidates: Sequence[float]) -> torch.Tensor:
     """fp32 [n_cand]: sum_rows dW_c H dW_c^T for every candidate scale factor, for the CUDA [N,K]
     weight W (this rank's row shard under sharding; the caller all-reduces)."""
-    assert W.is_cuda and W.dim() == 2 and H.shape == (W.shape[1], W.shape[1])
+    folded = isinstance(H, FoldedGram)
+    Hm = H.Hb if folded else H
+    assert W.is_cuda and W.dim() == 2 and Hm.shape == (W.shape[1], W.shape[1])
     import ctypes as C
     W = W.contiguous()
     N, K = W.shape
@@ -246,9 +351,9 @@ def awq_search_losses(W: torch.Tensor, H: torch.Tensor, salient_mask: torch.Tens
     mask = salient_mask.to(device=W.device, dtype=torch.uint8).contiguous()
     with _on(W.device):
         work = _workspace(W.device, lib.b200q_awq_search_workspace(N, K, n_cand))
-        rc = lib.b200q_awq_search_loss(W.data_ptr(), N, K, group, n_bit, mask.data_ptr(), sf, n_cand,
-                                       H.contiguous().data_ptr(), dtype_code(W), work.data_ptr(),
-                                       loss.data_ptr(), _stream())
+        fn = lib.b200q_awq_search_loss_folded if folded else lib.b200q_awq_search_loss
+        rc = fn(W.data_ptr(), N, K, group, n_bit, mask.data_ptr(), sf, n_cand,
+                Hm.contiguous().data_ptr(), dtype_code(W), work.data_ptr(), loss.data_ptr(), _stream())
     _lib.check(rc, "awq_search_loss")
     return loss
 
@@ -310,5 +415,5 @@ def gptq_hessian(input_feat: Sequence, in_features: int, device, perp_damp: floa
         H = hessian_accum(X, rows, H)
     if H is None:
         H = torch.zeros((K, K), dtype=torch.float32, device=device)
-    _dist.allreduce_sum(H)
+    allreduce_symmetric(H)
     return hessian_finalize(H, 1.0 / feats_total, perp_damp)

@@ -997,6 +997,80 @@ h_to_lower_bf16_kernel(const float* __restrict__ H, __nv_bfloat16* __restrict__ 
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Symmetric matrices between GPUs: the packed lower triangle.  X^T X partials are exactly symmetric
+// (the SYRK epilogue mirrors every tile), so ranks exchange row n as its columns 0..n, stored at
+// offset n(n+1)/2 -- half the bytes of the square.  For the AWQ search the folded operand
+// Hb[n][k] = H[n][k] + H[k][n] is then simply 2 P[n,k] off the diagonal: the fold runs on each
+// rank's reduce-scattered slice and the slices are all-gathered as bf16.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void packed_row_col(int64_t e, int64_t& n, int64_t& k) {
+  n = (int64_t)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+  while (n * (n + 1) / 2 > e) --n;
+  while ((n + 1) * (n + 2) / 2 <= e) ++n;
+  k = e - n * (n + 1) / 2;
+}
+
+// grid (ceil(K/256), K): row n, columns k <= n
+__global__ void __launch_bounds__(256)
+sym_pack_lower_kernel(const float* __restrict__ H, int64_t K, float* __restrict__ P) {
+  const int64_t n = blockIdx.y;
+  const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (k <= n) P[n * (n + 1) / 2 + k] = H[n * K + k];
+}
+
+// 32 x 32 tiles on and below the diagonal; off-diagonal tiles also write their mirror image
+__global__ void __launch_bounds__(256)
+sym_unpack_lower_kernel(const float* __restrict__ P, int64_t K, float* __restrict__ H) {
+  const int64_t bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t n0 = bi * 32, k0 = bj * 32;
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t n = n0 + i, k = k0 + tx;
+    float v = 0.f;
+    if (n < K && k < K) {
+      const int64_t hi = max(n, k), lo = min(n, k);
+      v = P[hi * (hi + 1) / 2 + lo];
+      H[n * K + k] = v;
+    }
+    tile[i][tx] = v;
+  }
+  if (bj == bi) return;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t k = k0 + i, n = n0 + tx;          // H[k][n] = tile[n - n0][k - k0]
+    if (n < K && k < K) H[k * K + n] = tile[tx][i];
+  }
+}
+
+// packed elements [e0, e1) -> bf16(2 P) off the diagonal, bf16(P) on it
+__global__ void __launch_bounds__(256)
+sym_fold_packed_kernel(const float* __restrict__ P, int64_t e0, int64_t e1, int64_t len,
+                       __nv_bfloat16* __restrict__ out) {
+  for (int64_t e = e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < e1;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (e < len) {
+      int64_t n, k;
+      packed_row_col(e, n, k);
+      v = P[e - e0];
+      if (k != n) v *= 2.f;
+    }
+    out[e - e0] = __float2bfloat16_rn(v);
+  }
+}
+
+// packed folded bf16 triangle -> [K,K] bf16, zeros above the diagonal; grid (ceil(K/256), K)
+__global__ void __launch_bounds__(256)
+sym_unpack_folded_kernel(const __nv_bfloat16* __restrict__ Pb, int64_t K,
+                         __nv_bfloat16* __restrict__ Hb) {
+  const int64_t n = blockIdx.y;
+  const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (k < K) Hb[n * K + k] = (k <= n) ? Pb[n * (n + 1) / 2 + k] : __float2bfloat16_rn(0.f);
+}
+
 // loss[c] (+)= sum over the tile rows of candidate c, fixed order, fp64 accumulate
 __global__ void awq_loss_reduce_kernel(const float* __restrict__ tile_loss, int tiles_per_cand,
                                        int n_cand, float* __restrict__ loss) {
@@ -1226,10 +1300,11 @@ int64_t b200q_awq_search_workspace(int64_t N, int64_t K, int n_cand) {
   return awq_layout(nullptr, N, K, n_cand).bytes;
 }
 
-int b200q_awq_search_loss(const void* W, int64_t N, int64_t K, int64_t group, int n_bit,
-                          const uint8_t* salient, const float* sf_host, int n_cand, const float* H,
-                          int dtype, void* work, float* loss, void* stream) {
-  B200Q_REQUIRE(W && salient && sf_host && H && work && loss, "awq_search_loss: null pointer");
+static int awq_search_impl(const void* W, int64_t N, int64_t K, int64_t group, int n_bit,
+                           const uint8_t* salient, const float* sf_host, int n_cand, const float* H,
+                           const __nv_bfloat16* Hb_folded, int dtype, void* work, float* loss,
+                           void* stream) {
+  B200Q_REQUIRE(W && salient && sf_host && (H || Hb_folded) && work && loss, "awq_search_loss: null pointer");
   B200Q_REQUIRE(N > 0 && K > 0, "awq_search_loss: bad shape");
   // the bf16 operands are read by TMA: 16-byte row pitch
   B200Q_REQUIRE(K % 8 == 0, "awq_search_loss: in_features must be a multiple of 8");
@@ -1246,16 +1321,20 @@ int b200q_awq_search_loss(const void* W, int64_t N, int64_t K, int64_t group, in
     rc = launch_awq_delta(W, w.D, salient, N, K, group, w.rows_pad * K, n_bit, sf_host, n_cand, dtype, st);
     if (rc != B200Q_OK) return rc;
   }
-  {
+  const __nv_bfloat16* Hb = Hb_folded;
+  if (Hb == nullptr) {
     KernelScope scope("awq_search_fold", 7.0 * K * K, 0, st);   // lower half: 8 B in + 2 B out; upper: 2 B out
     const unsigned tb = (unsigned)((K + 63) / 64);
     h_to_lower_bf16_kernel<<<dim3(tb, tb), 256, 0, st>>>(H, w.Hb, K);
     count_launch();
+    Hb = w.Hb;
+  } else {
+    B200Q_REQUIRE(aligned16(Hb), "awq_search_loss: unaligned folded operand");
   }
   CUtensorMap tmap_d, tmap_h;
   rc = make_tmap_bf16(&tmap_d, w.D, Mtot, K, ag::BM, ag::BK);
   if (rc != B200Q_OK) return rc;
-  rc = make_tmap_bf16(&tmap_h, w.Hb, K, K, ag::BN, ag::BK);
+  rc = make_tmap_bf16(&tmap_h, Hb, K, K, ag::BN, ag::BK);
   if (rc != B200Q_OK) return rc;
   cudaFuncSetAttribute(awq_loss_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        ag::SMEM_BYTES);
@@ -1272,6 +1351,65 @@ int b200q_awq_search_loss(const void* W, int64_t N, int64_t K, int64_t group, in
   awq_loss_reduce_kernel<<<n_cand, 256, 0, st>>>(w.tile_loss, 4 * w.tiles_per_cand, n_cand, loss);
   count_launch();
   return check_launch("awq_loss_reduce");
+}
+
+int b200q_awq_search_loss(const void* W, int64_t N, int64_t K, int64_t group, int n_bit,
+                          const uint8_t* salient, const float* sf_host, int n_cand, const float* H,
+                          int dtype, void* work, float* loss, void* stream) {
+  return awq_search_impl(W, N, K, group, n_bit, salient, sf_host, n_cand, H, nullptr, dtype, work, loss,
+                         stream);
+}
+
+int b200q_awq_search_loss_folded(const void* W, int64_t N, int64_t K, int64_t group, int n_bit,
+                                 const uint8_t* salient, const float* sf_host, int n_cand,
+                                 const void* Hb_folded, int dtype, void* work, float* loss,
+                                 void* stream) {
+  return awq_search_impl(W, N, K, group, n_bit, salient, sf_host, n_cand, nullptr,
+                         static_cast<const __nv_bfloat16*>(Hb_folded), dtype, work, loss, stream);
+}
+
+int64_t b200q_sym_packed_len(int64_t K) { return K > 0 ? K * (K + 1) / 2 : 0; }
+
+int b200q_sym_pack_lower(const float* H, int64_t K, float* P, void* stream) {
+  B200Q_REQUIRE(H && P && K > 0 && K < (1 << 30), "sym_pack_lower: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KernelScope scope("sym_pack", 4.0 * K * (K + 1), 0, st);
+  sym_pack_lower_kernel<<<dim3((unsigned)((K + 255) / 256), (unsigned)K), 256, 0, st>>>(H, K, P);
+  count_launch();
+  return check_launch("sym_pack_lower");
+}
+
+int b200q_sym_unpack_lower(const float* P, int64_t K, float* H, void* stream) {
+  B200Q_REQUIRE(H && P && K > 0 && K < (1 << 30), "sym_unpack_lower: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KernelScope scope("sym_unpack", 6.0 * K * K, 0, st);
+  const unsigned tb = (unsigned)((K + 31) / 32);
+  sym_unpack_lower_kernel<<<dim3(tb, tb), 256, 0, st>>>(P, K, H);
+  count_launch();
+  return check_launch("sym_unpack_lower");
+}
+
+int b200q_sym_fold_packed_bf16(const float* P_slice, int64_t K, int64_t e0, int64_t e1, void* out_bf16,
+                               void* stream) {
+  B200Q_REQUIRE(P_slice && out_bf16 && K > 0 && e0 >= 0 && e1 >= e0, "sym_fold_packed: bad argument");
+  if (e1 == e0) return B200Q_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KernelScope scope("sym_fold", 6.0 * (double)(e1 - e0), 0, st);
+  const int blocks = (int)std::min<int64_t>((e1 - e0 + 255) / 256, (int64_t)kNumSMs * 16);
+  sym_fold_packed_kernel<<<blocks, 256, 0, st>>>(P_slice, e0, e1, K * (K + 1) / 2,
+                                                 static_cast<__nv_bfloat16*>(out_bf16));
+  count_launch();
+  return check_launch("sym_fold_packed");
+}
+
+int b200q_sym_unpack_folded_bf16(const void* Pb, int64_t K, void* Hb, void* stream) {
+  B200Q_REQUIRE(Pb && Hb && K > 0 && K < (1 << 30), "sym_unpack_folded: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KernelScope scope("sym_unpack_folded", 3.0 * K * K, 0, st);
+  sym_unpack_folded_kernel<<<dim3((unsigned)((K + 255) / 256), (unsigned)K), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(Pb), K, static_cast<__nv_bfloat16*>(Hb));
+  count_launch();
+  return check_launch("sym_unpack_folded");
 }
 
 }  // extern "C"

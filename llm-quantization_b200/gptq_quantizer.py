@@ -35,9 +35,9 @@ from b200q import pipeline as _pipeline  # noqa: E402
 
 MODE = "parity"
 BUILD_HESSIAN = True
-GROUP_FACTOR = 4    # under row sharding, layers prepared together = GROUP_FACTOR * world size
+GROUP_FACTOR = 4    # under row sharding, layers prepared together = max(LOCAL_GROUP, GROUP_FACTOR * world size)
 FACTOR_STREAMS = 16 # Hessian inverses in flight at a time on one GPU (each on its own CUDA stream)
-LOCAL_GROUP = 16    # one GPU: layers prepared together (Hessians, then their inverses side by side)
+LOCAL_GROUP = 16    # layers prepared together (Hessians, then their inverses side by side)
 TIMINGS = None      # set to a list to collect (phase, ms) CUDA-event pairs from the model walker
 TRACE = None        # set to a list: (group start, begin, end, K) events of every concurrent inverse
 HOST_LAPS = None    # set to a dict to add up host seconds per walker phase (launch-side cost)
@@ -231,7 +231,7 @@ def gptq_quantize_model_weight(
         if name not in ready:
             i = position[name]
             world = _dist.world_size()
-            prepare(calibrated[i:i + (GROUP_FACTOR * world if world > 1 else max(1, LOCAL_GROUP))],
+            prepare(calibrated[i:i + max(1, LOCAL_GROUP, GROUP_FACTOR * world if world > 1 else 0)],
                     W.device)
         p = ready.pop(name)
         if p.done is not None or p.info_host is not None:

@@ -176,3 +176,45 @@ def test_search_accepts_what_the_reference_signature_accepts():
             best = aq.awq_search_scale_factor(net, 4, G, feats, n_grid=n_grid)
         assert isinstance(best, float) and 1.0 <= best <= 2.0
         assert any("left out of the search" in str(w.message) for w in rec)
+
+
+@pytest.mark.parametrize("K", [64, 200, 1000, 4096])
+def test_packed_triangle_exchange_kernels(K):
+    """The multi-GPU exchange format: pack / unpack of the lower triangle is lossless,
+    and folding reduce-scattered slices of the packed triangle gives the same bf16 search operand --
+    hence bit-identical losses -- as folding the square matrix on one GPU."""
+    from b200q import _lib, tensor_ops as T
+    g = torch.Generator().manual_seed(K)
+    A = torch.randn(K, K, generator=g)
+    H = ((A + A.T) / 2).cuda()
+    L = K * (K + 1) // 2
+    P = T.sym_pack_lower(H, pad_to=64)
+    assert P.numel() % 64 == 0 and P.numel() >= L
+    rows, cols = torch.tril_indices(K, K)
+    assert torch.equal(P[:L].cpu(), H.cpu()[rows, cols])
+    assert torch.equal(T.sym_unpack_lower(P, K), H)
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    want = (torch.tril(2 * H, -1) + torch.diag(torch.diag(H))).to(torch.bfloat16)
+    for w in (1, 2, 8):
+        Pw = T.sym_pack_lower(H, pad_to=8 * w)
+        Pw[L:] = float("nan")                                  # padding must never reach the result
+        per = Pw.numel() // w
+        Pb = torch.empty(Pw.numel(), dtype=torch.bfloat16, device="cuda")
+        for r in range(w):
+            sl = Pw[r * per:(r + 1) * per].contiguous()
+            assert lib.b200q_sym_fold_packed_bf16(sl.data_ptr(), K, r * per, (r + 1) * per,
+                                                  Pb[r * per:(r + 1) * per].data_ptr(), st) == 0
+        Hb = torch.empty((K, K), dtype=torch.bfloat16, device="cuda")
+        assert lib.b200q_sym_unpack_folded_bf16(Pb.data_ptr(), K, Hb.data_ptr(), st) == 0
+        assert torch.equal(Hb, want), w
+    if K % 8 == 0:
+        N = 256
+        W = (torch.randn(N, K, generator=g) * 0.02).cuda()
+        mask = torch.zeros(K, dtype=torch.uint8, device="cuda")
+        mask[:: max(1, K // 7)] = 1
+        cands = torch.linspace(1.0, 2.0, 6, dtype=torch.float64).tolist()
+        G = 128 if K % 128 == 0 else -1
+        a = T.awq_search_losses(W, H, mask, 4, G, cands)
+        b = T.awq_search_losses(W, T.FoldedGram(Hb), mask, 4, G, cands)
+        assert torch.equal(a, b)

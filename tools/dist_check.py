@@ -139,11 +139,27 @@ with torch.no_grad():
         full = kv(slice(0, Nkv))
         gptq_quantizer.gptq_quantize_model_weight(full, 3, 128, acts_kv, actorder=True, verbose=False)
         got = gather_kv(sh[0].weight.data)
-        agree = (got == full[0].weight.data.cpu()).float().mean().item()
-        ok = agree == 1.0 if mode == "parity" else agree >= 0.999
+        ref_out = full[0].weight.data.cpu()
+        agree = (got == ref_out).float().mean().item()
         if mode == "parity":
-            ok = ok and torch.equal(got, O.gptq_parity_quant(Wkv, 3)["out"])
-        results[f"llama3 k/v 1024x4096 w3 act-order, {mode}: {k1 - k0} rows/rank, agreement {agree:.5f}"] = ok
+            ok = agree == 1.0 and torch.equal(got, O.gptq_parity_quant(Wkv, 3)["out"])
+            note = f"agreement {agree:.5f}"
+        else:
+            # The all-reduced Hessian differs from the single-rank one in the last bits (summation
+            # order), which can swap neighbours in the act-order permutation argsort(diag(H)) and
+            # with them the order two columns are quantised in: a different, equally valid GPTQ run
+            # whose codes need not agree.  What must agree is the QUALITY: the output error
+            # tr(dW H dW^T) of the two runs, and both must beat round-to-nearest.
+            Hd = T.gptq_hessian(acts_kv["0"], Kkv, dev, 0.01, 128).double().cpu()
+            def out_err(Q):
+                D = Q.double() - Wkv.double()
+                return float(((D @ Hd) * D).sum())
+            e_sh, e_full = out_err(got), out_err(ref_out)
+            e_rtn = out_err(O.uniform_group_quant(Wkv, 3, 128)["out"])
+            ok = abs(e_sh - e_full) / e_full < 0.02 and e_sh < e_rtn and e_full < e_rtn
+            note = (f"code agreement {agree:.5f}, output error sharded / unsharded / round-to-nearest "
+                    f"{e_sh:.4e} / {e_full:.4e} / {e_rtn:.4e}")
+        results[f"llama3 k/v 1024x4096 w3 act-order, {mode}: {k1 - k0} rows/rank, {note}"] = ok
     gptq_quantizer.MODE = "parity"
 if rank == 0:
     print(f"dist_check: {world} ranks on {torch.cuda.get_device_name(0)}, NCCL {'.'.join(map(str, torch.cuda.nccl.version()))}")
