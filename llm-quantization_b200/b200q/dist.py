@@ -29,6 +29,7 @@ _active = False
 # every collective below is then bracketed by two CUDA events on the current stream and recorded as
 # (start, end, payload bytes).  None (the default) costs nothing.
 WAIT_EVENTS = None
+_on_comm_stream = False   # collectives issued on the communication stream stall THAT stream, not compute
 
 
 class _Timed:
@@ -39,7 +40,7 @@ class _Timed:
         self.e0 = None
 
     def __enter__(self):
-        if WAIT_EVENTS is not None and torch.cuda.is_available():
+        if WAIT_EVENTS is not None and not _on_comm_stream and torch.cuda.is_available():
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e0.record()
         return self
@@ -49,6 +50,21 @@ class _Timed:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             WAIT_EVENTS.append((self.e0, e1, self.nbytes))
+        return False
+
+
+class on_comm_stream:
+    """Marks collectives issued inside the block as running on a communication stream: their
+    duration is not compute-stream exposure (the consumer's timed_wait is)."""
+
+    def __enter__(self):
+        global _on_comm_stream
+        self._prev, _on_comm_stream = _on_comm_stream, True
+        return self
+
+    def __exit__(self, *exc):
+        global _on_comm_stream
+        _on_comm_stream = self._prev
         return False
 
 

@@ -175,6 +175,11 @@ PACKED_EXCHANGE = True     # False: plain fp32 [K,K] all-reduce (A/B timing, non
 _comm_streams = {}
 
 
+def comm_stream(device) -> torch.cuda.Stream:
+    """The per-device stream collectives are queued on when they should not block compute."""
+    return _comm_stream(torch.device(device))
+
+
 def _comm_stream(device) -> torch.cuda.Stream:
     s = _comm_streams.get(device.index)
     if s is None:
@@ -249,7 +254,7 @@ def _exchange_folded(H: torch.Tensor) -> PendingGram:
     Lp = P.numel()
     per = Lp // w
     comm.wait_stream(main)
-    with torch.cuda.stream(comm):
+    with torch.cuda.stream(comm), _dist.on_comm_stream():
         mine = torch.empty(per, dtype=torch.float32, device=dev)
         _dist.reduce_scatter_sum(mine, P)
         mine16 = torch.empty(per, dtype=torch.bfloat16, device=dev)
@@ -359,11 +364,17 @@ def awq_search_losses(W: torch.Tensor, H: torch.Tensor, salient_mask: torch.Tens
 
 
 def gptq_hessian(input_feat: Sequence, in_features: int, device, perp_damp: float = 0.01,
-                 nsamples: int = 128) -> torch.Tensor:
+                 nsamples: int = 128, defer_exchange: bool = False):
     """The damped Hessian of gptq_quantizer.py:133-150 as fp32 [K,K] on `device`:
     sum over input_feat[:nsamples] of x^T x / (||x|| + 1e-5)^2, divided by len(input_feat) (the
     FULL list length, as the reference does), plus perp_damp * I.  A [n, K] tensor stands for n
-    one-row samples (the reference iterates its rows); non-tensor features give I."""
+    one-row samples (the reference iterates its rows); non-tensor features give I.
+
+    defer_exchange (row sharding only): returns (H, event) instead of H -- the cross-rank sum of the
+    partial matrices (packed lower triangle), the unpacking and the scale / damping are queued on
+    the communication stream and `event` marks their completion, so the caller can go on with the
+    next layer's partial Hessian while this one is exchanged.  event is None when nothing was
+    deferred."""
     require_cuda()
     device = torch.device(device)
     K = in_features
@@ -372,8 +383,9 @@ def gptq_hessian(input_feat: Sequence, in_features: int, device, perp_damp: floa
         # batches were folded in as they were captured (streaming.py); `[:nsamples]` was applied by
         # the stream's max_batches, the divisor is every batch seen, as in the reference
         assert input_feat.normalize and input_feat.in_features == K
-        return hessian_finalize(input_feat.matrix_sum(device), 1.0 / max(1, input_feat.batches_seen),
-                                perp_damp)
+        Hs = hessian_finalize(input_feat.matrix_sum(device), 1.0 / max(1, input_feat.batches_seen),
+                              perp_damp)
+        return (Hs, None) if defer_exchange else Hs
     if isinstance(input_feat, torch.Tensor):
         feats_total = input_feat.shape[0]
         runs = [(input_feat[:nsamples].reshape(-1, K), 1)] if input_feat.dim() == 2 else \
@@ -382,7 +394,8 @@ def gptq_hessian(input_feat: Sequence, in_features: int, device, perp_damp: floa
         feats_total = len(input_feat)
         if feats_total == 0 or not isinstance(input_feat[0], torch.Tensor):
             H = torch.eye(K, dtype=torch.float32, device=device)
-            return hessian_finalize(H, 1.0 / max(1, feats_total), perp_damp)
+            H = hessian_finalize(H, 1.0 / max(1, feats_total), perp_damp)
+            return (H, None) if defer_exchange else H
         # group consecutive samples with the same number of rows into one call
         runs: List = []
         cur: List[torch.Tensor] = []
@@ -415,5 +428,20 @@ def gptq_hessian(input_feat: Sequence, in_features: int, device, perp_damp: floa
         H = hessian_accum(X, rows, H)
     if H is None:
         H = torch.zeros((K, K), dtype=torch.float32, device=device)
+    if defer_exchange and _dist.is_sharded() and PACKED_EXCHANGE:
+        main = torch.cuda.current_stream(device)
+        comm = _comm_stream(device)
+        P = sym_pack_lower(H)
+        comm.wait_stream(main)
+        with torch.cuda.stream(comm), _dist.on_comm_stream():
+            _dist.allreduce_sum(P)
+            sym_unpack_lower(P, K, out=H)
+            hessian_finalize(H, 1.0 / feats_total, perp_damp)
+            ev = torch.cuda.Event()
+            ev.record(comm)
+        P.record_stream(comm)
+        H.record_stream(comm)
+        return H, ev
     allreduce_symmetric(H)
-    return hessian_finalize(H, 1.0 / feats_total, perp_damp)
+    H = hessian_finalize(H, 1.0 / feats_total, perp_damp)
+    return (H, None) if defer_exchange else H

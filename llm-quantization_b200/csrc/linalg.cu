@@ -493,7 +493,10 @@ static int cholesky_and_inverse(cudaStream_t st, const LinalgWork& w, int64_t K,
     const auto key = std::make_tuple(dev, static_cast<const void*>(w.A), K);
     auto it = g_graphs.find(key);
     if (it == g_graphs.end()) {
-      if (g_graphs.size() >= 32) {               // workspaces come and go: do not hoard graphs
+      // One graph per (workspace, size): the model walker keeps up to 16 streams' workspaces busy with
+      // two or three matrix sizes each, so well over 32 graphs are live at a time -- re-capturing
+      // (tens of ms of host time per graph) must only happen when workspaces really come and go.
+      if (g_graphs.size() >= 256) {
         for (auto& kv : g_graphs) cudaGraphExecDestroy(kv.second.exec);
         g_graphs.clear();
       }

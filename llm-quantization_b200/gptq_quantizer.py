@@ -35,9 +35,8 @@ from b200q import pipeline as _pipeline  # noqa: E402
 
 MODE = "parity"
 BUILD_HESSIAN = True
-GROUP_FACTOR = 4    # under row sharding, layers prepared together = max(LOCAL_GROUP, GROUP_FACTOR * world size)
 FACTOR_STREAMS = 16 # Hessian inverses in flight at a time on one GPU (each on its own CUDA stream)
-LOCAL_GROUP = 16    # layers prepared together (Hessians, then their inverses side by side)
+LOCAL_GROUP = 16    # layers prepared together PER RANK (Hessians, then their inverses side by side)
 TIMINGS = None      # set to a list to collect (phase, ms) CUDA-event pairs from the model walker
 TRACE = None        # set to a list: (group start, begin, end, K) events of every concurrent inverse
 HOST_LAPS = None    # set to a dict to add up host seconds per walker phase (launch-side cost)
@@ -124,7 +123,12 @@ def gptq_quantize_model_weight(
             slots[k] = b
         return b
 
+    in_flight: List[torch.cuda.Event] = []  # broadcasts of the previous group (parity mode)
+
     def retire():
+        for ev in in_flight:
+            torch.cuda.current_stream().wait_event(ev)
+        in_flight.clear()
         for p in retiring:
             p.check()
         retiring.clear()
@@ -193,8 +197,20 @@ def gptq_quantize_model_weight(
         world = _dist.world_size()
         owner = _deal_layers([(n, m.weight.shape[1]) for n, m in group], world)
         t0 = _mark()
-        hessians = [_hessian_stage(input_feat[n], m.weight.shape[1], device, perp_damp, nsamples)
-                    for n, m in group]
+        # (under sharding each layer's exchange -- packed all-reduce, unpack, damping -- runs on the
+        # communication stream while the next layer's partial Hessian is computed)
+        main = torch.cuda.current_stream(device)
+        hessians, pending = [], []
+        for n, m in group:
+            H, ev = _hessian_stage(input_feat[n], m.weight.shape[1], device, perp_damp, nsamples,
+                                   defer_exchange=True)
+            hessians.append(H)
+            if ev is not None:
+                pending.append((ev, H))
+        if pending:
+            with _dist.timed_wait(sum(2 * H.numel() for _e, H in pending)):
+                for ev, _H in pending:
+                    main.wait_event(ev)
         t1 = _mark()
         import time as _time
         h0 = _time.perf_counter()
@@ -206,12 +222,28 @@ def gptq_quantize_model_weight(
             HOST_LAPS["factor launch"] = HOST_LAPS.get("factor launch", 0.0) + (_time.perf_counter() - h1)
         t2 = _mark()
         if world > 1:
+            # The factors go out on the communication stream.  Parity mode never reads H^-1
+            # (gptq_quantizer.py:189-194): the column stages and the next group's Hessians run
+            # while the broadcasts are in flight and the group is joined when it retires;
+            # compensated mode waits before its column stages.
+            from b200q import tensor_ops as _tops
+            comm = _tops.comm_stream(device)
+            comm.wait_stream(main)
             flags = []
-            for p in prepared:
-                if p.factor is not None:
-                    _dist.broadcast(p.factor, owner[p.name])
-                    flags.append(p.info)
-                    p.done = p.info_host = None
+            with torch.cuda.stream(comm), _dist.on_comm_stream():
+                for p in prepared:
+                    if p.factor is not None:
+                        _dist.broadcast(p.factor, owner[p.name])
+                        p.factor.record_stream(comm)
+                        flags.append(p.info)
+                        p.done = p.info_host = None
+                sent = torch.cuda.Event()
+                sent.record(comm)
+            if MODE == "compensated":
+                with _dist.timed_wait(sum(4 * p.factor.numel() for p in prepared if p.factor is not None)):
+                    main.wait_event(sent)
+            else:
+                in_flight.append(sent)
             if flags:
                 # one status exchange and one host sync for the whole group: every rank sees every
                 # owner's flag, so all ranks warn / raise together
@@ -231,7 +263,7 @@ def gptq_quantize_model_weight(
         if name not in ready:
             i = position[name]
             world = _dist.world_size()
-            prepare(calibrated[i:i + max(1, LOCAL_GROUP, GROUP_FACTOR * world if world > 1 else 0)],
+            prepare(calibrated[i:i + max(1, LOCAL_GROUP * max(1, world))],
                     W.device)
         p = ready.pop(name)
         if p.done is not None or p.info_host is not None:
@@ -349,22 +381,27 @@ def _gptq_quantize_layer(
     layer.weight.data = out if out.device == src else out.to(src)
 
 
-def _hessian_stage(input_feat, K: int, device, perp_damp: float, nsamples: int):
+def _hessian_stage(input_feat, K: int, device, perp_damp: float, nsamples: int,
+                   defer_exchange: bool = False):
     """The damped Hessian of one layer (all-reduced under row sharding), or None when parity mode
-    is told to skip the work the reference's output does not depend on."""
+    is told to skip the work the reference's output does not depend on.  defer_exchange: returns
+    (H, event) with the cross-rank exchange queued on the communication stream (see
+    tensor_ops.gptq_hessian); event is None when there is nothing to wait for."""
     if MODE not in ("parity", "compensated"):
         raise ValueError(f"gptq_quantizer.MODE must be 'parity' or 'compensated', got {MODE!r}")
-    if MODE == "parity" and not BUILD_HESSIAN:
-        return None
-    if K % 8 != 0:
+    skip = MODE == "parity" and not BUILD_HESSIAN
+    if not skip and K % 8 != 0:
         # the tensor-core Hessian kernel reads the activations by TMA (16-byte row pitch)
         if MODE == "compensated":
             raise NotImplementedError(f"compensated GPTQ needs in_features % 8 == 0, got {K}")
         import warnings
         warnings.warn(f"gptq: in_features = {K} is not a multiple of 8; H and H^-1 (which the "
                       f"reference-parity output does not read) are not built for this layer")
-        return None
-    return gptq_hessian(input_feat, K, device, perp_damp, nsamples)
+        skip = True
+    if skip:
+        return (None, None) if defer_exchange else None
+    from b200q import tensor_ops as _tops
+    return _tops.gptq_hessian(input_feat, K, device, perp_damp, nsamples, defer_exchange=defer_exchange)
 
 
 def _factor_stage(name: str, H, actorder: bool, owner: int = 0, buffers=None) -> _Prepared:
