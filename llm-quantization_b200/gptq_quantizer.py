@@ -125,10 +125,20 @@ def gptq_quantize_model_weight(
 
     in_flight: List[torch.cuda.Event] = []  # broadcasts of the previous group (parity mode)
 
+    group_status: List[tuple] = []          # (event, pinned flags, [(name, K)]) of sharded groups
+
+    def check_group_status():
+        for seen, host, layers in group_status:
+            seen.synchronize()
+            for (name, K), j in zip(layers, host.tolist()):
+                _report_pivot(int(j), K, name)
+        group_status.clear()
+
     def retire():
         for ev in in_flight:
             torch.cuda.current_stream().wait_event(ev)
         in_flight.clear()
+        check_group_status()
         for p in retiring:
             p.check()
         retiring.clear()
@@ -227,30 +237,35 @@ def gptq_quantize_model_weight(
             # while the broadcasts are in flight and the group is joined when it retires;
             # compensated mode waits before its column stages.
             from b200q import tensor_ops as _tops
+            owned = [p for p in prepared if p.factor is not None]
+            if owned:
+                # one status exchange for the whole group, BEFORE the broadcasts are queued (NCCL runs
+                # a communicator's collectives in order): every rank gets every owner's flag, so all
+                # ranks warn / raise together -- one group later, from pinned memory, without a host
+                # sync here
+                status = _dist.allreduce_max(torch.cat([p.info for p in owned]))
+                lo = position[owned[0].name]
+                host = flags_host[lo:lo + len(owned)] if lo + len(owned) <= flags_host.numel() else \
+                    torch.empty(len(owned), dtype=torch.int32).pin_memory()
+                host.copy_(status, non_blocking=True)
+                seen = torch.cuda.Event()
+                seen.record(main)
+                group_status.append((seen, host, [(p.name, p.K) for p in owned]))
             comm = _tops.comm_stream(device)
             comm.wait_stream(main)
-            flags = []
             with torch.cuda.stream(comm), _dist.on_comm_stream():
-                for p in prepared:
-                    if p.factor is not None:
-                        _dist.broadcast(p.factor, owner[p.name])
-                        p.factor.record_stream(comm)
-                        flags.append(p.info)
-                        p.done = p.info_host = None
+                for p in owned:
+                    _dist.broadcast(p.factor, owner[p.name])
+                    p.factor.record_stream(comm)
+                    p.done = p.info_host = p.info = None
                 sent = torch.cuda.Event()
                 sent.record(comm)
             if MODE == "compensated":
-                with _dist.timed_wait(sum(4 * p.factor.numel() for p in prepared if p.factor is not None)):
+                with _dist.timed_wait(sum(4 * p.factor.numel() for p in owned)):
                     main.wait_event(sent)
+                check_group_status()          # the column stages multiply by the factors
             else:
                 in_flight.append(sent)
-            if flags:
-                # one status exchange and one host sync for the whole group: every rank sees every
-                # owner's flag, so all ranks warn / raise together
-                status = _dist.allreduce_max(torch.cat(flags))
-                for p, j in zip([p for p in prepared if p.factor is not None], status.tolist()):
-                    p.info = None
-                    _report_pivot(int(j), p.K, p.name)
         for p in prepared:
             ready[p.name] = p
         _lap("hessians", t0, t1)
