@@ -68,6 +68,10 @@ MODELS = {
                   ("lm_head", 128256, 4096, 1)],
     "opt-125m": [("attn.qkvo", 768, 768, 48), ("fc1", 3072, 768, 12), ("fc2", 768, 3072, 12),
                  ("lm_head", 50272, 768, 1)],
+    # one transformer block of Llama-2-7B (the model is 32 of these plus lm_head): the unit the ncu
+    # launch list is taken on -- the factorisation graphs alone are ~1100 kernels per Linear
+    "llama2-7b-block": [("attn.qkvo", 4096, 4096, 4), ("mlp.gate_up", 11008, 4096, 2),
+                        ("mlp.down", 4096, 11008, 1)],
     "tiny": [("a", 512, 1024, 4), ("b", 1024, 512, 2)],
 }
 W_BIT, GROUP = 4, 128

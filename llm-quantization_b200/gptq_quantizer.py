@@ -126,6 +126,7 @@ def gptq_quantize_model_weight(
     in_flight: List[torch.cuda.Event] = []  # broadcasts of the previous group (parity mode)
 
     group_status: List[tuple] = []          # (event, pinned flags, [(name, K)]) of sharded groups
+    colmax_ready: Dict[str, torch.Tensor] = {}   # all-reduced column |max| of a group's resident layers
 
     def check_group_status():
         for seen, host, layers in group_status:
@@ -266,6 +267,22 @@ def gptq_quantize_model_weight(
                 check_group_status()          # the column stages multiply by the factors
             else:
                 in_flight.append(sent)
+        if world > 1 and MODE == "parity":
+            # The reference's column scale spans ALL rows (:182): the shards' column maxima are
+            # combined with an all-reduce MAX.  For the device-resident layers of the group that is
+            # ONE collective over the concatenated [sum K] vector instead of one per layer (at 8
+            # GPUs the per-layer launches and waits were a fifth of the step).
+            resident = [(n, m) for n, m in group if m.weight.is_cuda]
+            if resident:
+                sizes = [m.weight.shape[1] for _n, m in resident]
+                padded = [(k + 3) // 4 * 4 for k in sizes]           # 16-byte aligned slices
+                flat = torch.zeros(sum(padded), dtype=torch.float32, device=device)
+                views = [c[:k] for c, k in zip(flat.split(padded), sizes)]
+                for (_n, m), v in zip(resident, views):
+                    _ops.col_absmax(m.weight.data, out=v)
+                _dist.allreduce_max(flat)
+                for (n, _m), v in zip(resident, views):
+                    colmax_ready[n] = v
         for p in prepared:
             ready[p.name] = p
         _lap("hessians", t0, t1)
@@ -287,7 +304,8 @@ def gptq_quantize_model_weight(
             else:
                 retiring.append(p)    # parity output does not read H^-1: look at the flag later
         t2 = _mark()
-        out = _column_stage(W, w_bit, q_group_size, blocksize, p.H, p.perm, p.factor)
+        out = _column_stage(W, w_bit, q_group_size, blocksize, p.H, p.perm, p.factor,
+                            colmax=colmax_ready.pop(name, None))
         _lap("columns", t2, _mark())
         return out
 
@@ -452,7 +470,7 @@ def _gptq_device(W: torch.Tensor, n_bit: int, q_group_size: int, input_feat, per
 
 
 def _column_stage(W: torch.Tensor, n_bit: int, q_group_size: int, blocksize: int, H, perm,
-                  factor) -> torch.Tensor:
+                  factor, colmax=None) -> torch.Tensor:
     if MODE == "compensated":
         from b200q import tensor_ops as _tops
         out = _tops.gptq_compensated(W, None, n_bit, q_group_size, blocksize, perm, U=factor)
@@ -461,7 +479,8 @@ def _column_stage(W: torch.Tensor, n_bit: int, q_group_size: int, blocksize: int
         # writes q*s back; permuting and un-permuting independent columns is the identity.
         if _dist.is_sharded():
             # the column scale spans ALL rows (:182): combine the shards' column maxima first
-            colmax = _dist.allreduce_max(_ops.col_absmax(W))
+            if colmax is None:
+                colmax = _dist.allreduce_max(_ops.col_absmax(W))
             out = _ops.gptq_parity_quant(W, n_bit, colmax)
         else:
             out = _ops.gptq_parity_layer(W, n_bit)          # both kernels behind one host call
