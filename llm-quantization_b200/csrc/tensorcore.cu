@@ -424,15 +424,16 @@ constexpr int B_BYTES = 2 * BOX_BYTES;                      // this CTA's 128 ch
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;              // 32 KiB per CTA
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 constexpr int THREADS = 256;
-constexpr int RASTER_M = 8;      // 256-row tile rows per rasterisation band
+constexpr int RASTER_M_DEFAULT = 8;   // 256-row tile rows per rasterisation band
 }  // namespace hg2
 
 template <bool BF16, bool PER_SAMPLE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(hg2::THREADS, 1)
 hessian_gemm2_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ partial,
                      int64_t K, int64_t T, int64_t tokens_per_split, int tiles_n,
-                     const float* __restrict__ norms, int kb_per_sample) {
+                     const float* __restrict__ norms, int kb_per_sample, int raster_m) {
   using namespace hg2;
+  const int RASTER_M = raster_m;
   constexpr uint32_t kTmemCols = PER_SAMPLE ? 512u : 256u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -716,6 +717,12 @@ static bool hessian_pair() {
 }
 
 static int hessian_splits(int64_t K, int64_t T, bool straight) {
+  static const int forced = []() {
+    const char* e = std::getenv("B200Q_HESSIAN_SPLITS");     // experiments only
+    const int v = e != nullptr ? std::atoi(e) : 0;
+    return (v >= 1 && v <= 16) ? v : 0;
+  }();
+  if (forced > 0) return forced;
   const bool pair = hessian_pair();
   const int64_t bm = pair ? hg2::BM : hg::BM;
   const int64_t tm = (K + bm - 1) / bm, tn = (K + hg::BN - 1) / hg::BN;
@@ -1241,6 +1248,15 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
   {
     KernelScope scope("hessian_gemm", 0, flops, st);
     const bool pair = hessian_pair();
+    // band height of the pair kernel's tile order, in 256-row tile rows (B200Q_HESSIAN_RASTER
+    // overrides, read per call).  Interleaved A/B at 262144 tokens: K = 11008 runs 27.9 ms with
+    // bands of 4, 29.1 with 8, 32.2 with 16; K = 4096 (16 tile rows) is flat within 3 %.
+    const int raster_m = [&]() {
+      const char* e = std::getenv("B200Q_HESSIAN_RASTER");
+      const int v = e != nullptr ? std::atoi(e) : 0;
+      if (v >= 1 && v <= 64) return v;
+      return (K > 6144) ? 4 : hg2::RASTER_M_DEFAULT;
+    }();
     const int tiles_n = (int)((K + hg::BN - 1) / hg::BN);
     const int tiles_m = (int)((K + (pair ? hg2::BM : hg::BM) - 1) / (pair ? hg2::BM : hg::BM));
     // pairs: two CTAs (one cluster) per 256 x 256 tile
@@ -1250,7 +1266,7 @@ int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, i
     do {                                                                                          \
       if (pair)                                                                                   \
         hessian_gemm2_kernel<BF, PS><<<grid, hg2::THREADS, hg2::SMEM_BYTES, st>>>(                 \
-            tmap, gemm_out, K, T, tokens_per_split, tiles_n, norms, kb_per_sample);               \
+            tmap, gemm_out, K, T, tokens_per_split, tiles_n, norms, kb_per_sample, raster_m);     \
       else                                                                                        \
         hessian_gemm_kernel<BF, PS><<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(                    \
             tmap, gemm_out, K, T, tokens_per_split, tiles_n, norms, kb_per_sample);               \
