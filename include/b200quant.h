@@ -269,6 +269,17 @@ int b200q_awq_search_loss_folded(const void* W, int64_t N, int64_t K, int64_t gr
                                  const uint8_t* salient, const float* sf_host, int n_cand,
                                  const void* Hb_folded, int dtype, void* work, float* loss,
                                  void* stream);
+/* the two halves of b200q_awq_search_loss as separate calls, so that a caller can run the
+ * candidate quantisation (which needs only W and the salient mask) on another stream WHILE the Gram
+ * matrix is still being computed: _delta fills the workspace with dW_c = Q_c(W) - W (bf16) for all
+ * candidates; _loss_prepared folds H (or takes Hb_folded; pass exactly one of the two), runs the
+ * loss GEMM on the workspace and adds the per-candidate losses.  Same workspace, same N, K, n_cand
+ * in both calls; the caller orders them. */
+int b200q_awq_search_delta(const void* W, int64_t N, int64_t K, int64_t group, int n_bit,
+                           const uint8_t* salient, const float* sf_host, int n_cand, int dtype,
+                           void* work, void* stream);
+int b200q_awq_search_loss_prepared(int64_t N, int64_t K, int n_cand, const float* H,
+                                   const void* Hb_folded, void* work, float* loss, void* stream);
 
 /* ---- symmetric [K,K] matrices between GPUs: the packed lower triangle (new) -----
  * X^T X partial sums (ref: gptq_quantizer.py:144 accumulated over calibration samples dealt to

@@ -68,6 +68,9 @@ SIGNATURES = {
     "b200q_awq_search_loss_folded": (C.c_int, [c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp,
                                                C.POINTER(C.c_float), C.c_int, c_vp, C.c_int, c_vp, c_fp,
                                                c_vp]),
+    "b200q_awq_search_delta": (C.c_int, [c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp, C.POINTER(C.c_float),
+                                         C.c_int, C.c_int, c_vp, c_vp]),
+    "b200q_awq_search_loss_prepared": (C.c_int, [c_i64, c_i64, C.c_int, c_fp, c_vp, c_vp, c_fp, c_vp]),
     "b200q_sym_packed_len": (c_i64, [c_i64]),
     "b200q_sym_pack_lower": (C.c_int, [c_fp, c_i64, c_fp, c_vp]),
     "b200q_sym_unpack_lower": (C.c_int, [c_fp, c_i64, c_fp, c_vp]),

@@ -363,6 +363,56 @@ def awq_search_losses(W: torch.Tensor, H: torch.Tensor, salient_mask: torch.Tens
     return loss
 
 
+class PreparedSearch:
+    """dW_c for every candidate of one layer, sitting in a workspace (awq_search_prepare)."""
+    __slots__ = ("work", "N", "K", "n_cand", "device")
+
+    def __init__(self, work, N, K, n_cand, device):
+        self.work, self.N, self.K, self.n_cand, self.device = work, N, K, n_cand, device
+
+
+_search_work = {}
+
+
+def awq_search_prepare(W: torch.Tensor, salient_mask: torch.Tensor, n_bit: int, group: int,
+                       candidates: Sequence[float]) -> PreparedSearch:
+    """First half of awq_search_losses: quantise W for every candidate and keep dW_c (bf16) in a
+    per-device workspace.  Needs no Gram matrix, so it can run on a side stream while the Gram GEMM
+    is still busy; awq_search_finish consumes it (the caller orders the two with events)."""
+    assert W.is_cuda and W.dim() == 2
+    import ctypes as C
+    W = W.contiguous()
+    N, K = W.shape
+    n_cand = len(candidates)
+    lib = _lib.load()
+    nbytes = lib.b200q_awq_search_workspace(N, K, n_cand)
+    buf = _search_work.get(W.device.index)
+    if buf is None or buf.numel() < nbytes:
+        buf = _search_work[W.device.index] = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
+    sf = (C.c_float * n_cand)(*[float(c) for c in candidates])
+    mask = salient_mask.to(device=W.device, dtype=torch.uint8).contiguous()
+    with _on(W.device):
+        rc = lib.b200q_awq_search_delta(W.data_ptr(), N, K, group, n_bit, mask.data_ptr(), sf, n_cand,
+                                        dtype_code(W), buf.data_ptr(), _stream())
+    _lib.check(rc, "awq_search_delta")
+    return PreparedSearch(buf, N, K, n_cand, W.device)
+
+
+def awq_search_finish(p: PreparedSearch, H) -> torch.Tensor:
+    """Second half: fp32 [n_cand] losses sum_rows dW_c H dW_c^T from a prepared workspace and the
+    Gram matrix (fp32 [K,K], or a FoldedGram)."""
+    folded = isinstance(H, FoldedGram)
+    Hm = (H.Hb if folded else H).contiguous()
+    assert Hm.shape == (p.K, p.K)
+    loss = torch.zeros(p.n_cand, dtype=torch.float32, device=p.device)
+    with _on(p.device):
+        rc = _lib.load().b200q_awq_search_loss_prepared(p.N, p.K, p.n_cand, None if folded else Hm.data_ptr(),
+                                                        Hm.data_ptr() if folded else None,
+                                                        p.work.data_ptr(), loss.data_ptr(), _stream())
+    _lib.check(rc, "awq_search_loss_prepared")
+    return loss
+
+
 def gptq_hessian(input_feat: Sequence, in_features: int, device, perp_damp: float = 0.01,
                  nsamples: int = 128, defer_exchange: bool = False):
     """The damped Hessian of gptq_quantizer.py:133-150 as fp32 [K,K] on `device`:

@@ -8,6 +8,8 @@
 // eager op sequence exactly (IEEE div, rint = half-to-even, no FMA contraction: this file is
 // compiled with -fmad=false), so fp32 results are bit-identical to the reference's.
 #include <algorithm>
+#include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -1052,6 +1054,42 @@ topk_colmul_kernel(const float* __restrict__ v, int K, int k, float factor, floa
 // =================================================================================================
 using namespace b200q;
 
+// The AWQ search runs these kernels on a side stream WHILE a tcgen05 GEMM (197 KB of dynamic
+// shared memory per CTA, i.e. the maximum shared-memory carveout) occupies every SM.  Blocks of two
+// kernels only share an SM if both run under the same L1 / shared-memory split, so the kernels
+// that are meant to fill the GEMM's idle issue slots ask for the same (maximum-shared) carveout.
+template <typename K>
+static void prefer_max_shared(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                       cudaSharedmemCarveoutMaxShared);
+}
+static void side_stream_kernels_share_the_gemm_carveout() {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 0 || dev >= 64 || done[dev]) return;
+  done[dev] = true;
+  const char* e = std::getenv("B200Q_SIDE_CARVEOUT");
+  if (e == nullptr || e[0] != '1') return;
+  prefer_max_shared(act_abssum_partial_kernel<float>);
+  prefer_max_shared(act_abssum_partial_kernel<__half>);
+  prefer_max_shared(act_abssum_partial_kernel<__nv_bfloat16>);
+  prefer_max_shared(act_mean_finish_kernel<float>);
+  prefer_max_shared(act_mean_finish_kernel<__half>);
+  prefer_max_shared(act_mean_finish_kernel<__nv_bfloat16>);
+  prefer_max_shared(seq_sum_rows_kernel<float>);
+  prefer_max_shared(seq_sum_rows_kernel<__half>);
+  prefer_max_shared(seq_sum_rows_kernel<__nv_bfloat16>);
+  prefer_max_shared(topk_colmul_kernel);
+  prefer_max_shared(awq_delta128_kernel<float>);
+  prefer_max_shared(awq_delta128_kernel<__half>);
+  prefer_max_shared(awq_delta128_kernel<__nv_bfloat16>);
+  cudaGetLastError();
+  done[dev] = true;
+}
+
 extern "C" {
 
 int b200q_col_absmax(const void* W, int64_t N, int64_t K, int64_t ld, int dtype, float* colmax,
@@ -1222,6 +1260,7 @@ int b200q_act_meanabs_batched(const void* X, int n_samples, int64_t rows_per_sam
   B200Q_REQUIRE(n_samples <= 65535, "act_meanabs: too many samples");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t T = rows_per_sample;
+  side_stream_kernels_share_the_gemm_carveout();
   KernelScope scope("act_meanabs", (double)n_samples * T * K * elem_size(dtype), 0, st);
   B200Q_DISPATCH_DTYPE(dtype, Tt, {
     constexpr int VEC = ST<Tt>::VEC;

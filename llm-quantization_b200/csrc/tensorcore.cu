@@ -1316,27 +1316,35 @@ int64_t b200q_awq_search_workspace(int64_t N, int64_t K, int n_cand) {
   return awq_layout(nullptr, N, K, n_cand).bytes;
 }
 
-static int awq_search_impl(const void* W, int64_t N, int64_t K, int64_t group, int n_bit,
-                           const uint8_t* salient, const float* sf_host, int n_cand, const float* H,
-                           const __nv_bfloat16* Hb_folded, int dtype, void* work, float* loss,
-                           void* stream) {
-  B200Q_REQUIRE(W && salient && sf_host && (H || Hb_folded) && work && loss, "awq_search_loss: null pointer");
-  B200Q_REQUIRE(N > 0 && K > 0, "awq_search_loss: bad shape");
+// stage 1: dW_c = Q_c(W) - W for every candidate, bf16, into the workspace
+static int awq_search_delta_stage(const void* W, int64_t N, int64_t K, int64_t group, int n_bit,
+                                  const uint8_t* salient, const float* sf_host, int n_cand, int dtype,
+                                  void* work, void* stream) {
+  B200Q_REQUIRE(W && salient && sf_host && work, "awq_search: null pointer");
+  B200Q_REQUIRE(N > 0 && K > 0, "awq_search: bad shape");
   // the bf16 operands are read by TMA: 16-byte row pitch
-  B200Q_REQUIRE(K % 8 == 0, "awq_search_loss: in_features must be a multiple of 8");
+  B200Q_REQUIRE(K % 8 == 0, "awq_search: in_features must be a multiple of 8");
+  B200Q_REQUIRE(aligned16(work), "awq_search: unaligned workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AwqWork w = awq_layout(work, N, K, n_cand);
+  const int64_t Mtot = (int64_t)n_cand * w.rows_pad;
+  KernelScope scope("awq_search_delta", (double)N * K * (elem_size(dtype) + 2.0 * n_cand), 0, st);
+  if (w.rows_pad != N)   // padding rows must be zero: they are read by the GEMM
+    cudaMemsetAsync(w.D, 0, 2 * Mtot * K, st);
+  return launch_awq_delta(W, w.D, salient, N, K, group, w.rows_pad * K, n_bit, sf_host, n_cand, dtype, st);
+}
+
+// stage 2: fold H (unless the caller supplies the folded operand), the loss GEMM, the reduction
+static int awq_search_loss_stage(int64_t N, int64_t K, int n_cand, const float* H,
+                                 const __nv_bfloat16* Hb_folded, void* work, float* loss,
+                                 void* stream) {
+  B200Q_REQUIRE((H || Hb_folded) && work && loss, "awq_search_loss: null pointer");
+  B200Q_REQUIRE(N > 0 && K > 0 && K % 8 == 0 && n_cand >= 1, "awq_search_loss: bad shape");
   B200Q_REQUIRE(aligned16(work), "awq_search_loss: unaligned workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   AwqWork w = awq_layout(work, N, K, n_cand);
   const int64_t Mtot = (int64_t)n_cand * w.rows_pad;
   int rc;
-  {
-    KernelScope scope("awq_search_delta",
-                      (double)N * K * (elem_size(dtype) + 2.0 * n_cand), 0, st);
-    if (w.rows_pad != N)   // padding rows must be zero: they are read by the GEMM
-      cudaMemsetAsync(w.D, 0, 2 * Mtot * K, st);
-    rc = launch_awq_delta(W, w.D, salient, N, K, group, w.rows_pad * K, n_bit, sf_host, n_cand, dtype, st);
-    if (rc != B200Q_OK) return rc;
-  }
   const __nv_bfloat16* Hb = Hb_folded;
   if (Hb == nullptr) {
     KernelScope scope("awq_search_fold", 7.0 * K * K, 0, st);   // lower half: 8 B in + 2 B out; upper: 2 B out
@@ -1372,16 +1380,33 @@ static int awq_search_impl(const void* W, int64_t N, int64_t K, int64_t group, i
 int b200q_awq_search_loss(const void* W, int64_t N, int64_t K, int64_t group, int n_bit,
                           const uint8_t* salient, const float* sf_host, int n_cand, const float* H,
                           int dtype, void* work, float* loss, void* stream) {
-  return awq_search_impl(W, N, K, group, n_bit, salient, sf_host, n_cand, H, nullptr, dtype, work, loss,
-                         stream);
+  B200Q_REQUIRE(H, "awq_search_loss: null pointer");
+  int rc = awq_search_delta_stage(W, N, K, group, n_bit, salient, sf_host, n_cand, dtype, work, stream);
+  if (rc != B200Q_OK) return rc;
+  return awq_search_loss_stage(N, K, n_cand, H, nullptr, work, loss, stream);
 }
 
 int b200q_awq_search_loss_folded(const void* W, int64_t N, int64_t K, int64_t group, int n_bit,
                                  const uint8_t* salient, const float* sf_host, int n_cand,
                                  const void* Hb_folded, int dtype, void* work, float* loss,
                                  void* stream) {
-  return awq_search_impl(W, N, K, group, n_bit, salient, sf_host, n_cand, nullptr,
-                         static_cast<const __nv_bfloat16*>(Hb_folded), dtype, work, loss, stream);
+  B200Q_REQUIRE(Hb_folded, "awq_search_loss: null pointer");
+  int rc = awq_search_delta_stage(W, N, K, group, n_bit, salient, sf_host, n_cand, dtype, work, stream);
+  if (rc != B200Q_OK) return rc;
+  return awq_search_loss_stage(N, K, n_cand, nullptr, static_cast<const __nv_bfloat16*>(Hb_folded), work,
+                               loss, stream);
+}
+
+int b200q_awq_search_delta(const void* W, int64_t N, int64_t K, int64_t group, int n_bit,
+                           const uint8_t* salient, const float* sf_host, int n_cand, int dtype,
+                           void* work, void* stream) {
+  return awq_search_delta_stage(W, N, K, group, n_bit, salient, sf_host, n_cand, dtype, work, stream);
+}
+
+int b200q_awq_search_loss_prepared(int64_t N, int64_t K, int n_cand, const float* H,
+                                   const void* Hb_folded, void* work, float* loss, void* stream) {
+  return awq_search_loss_stage(N, K, n_cand, H, static_cast<const __nv_bfloat16*>(Hb_folded), work, loss,
+                               stream);
 }
 
 int64_t b200q_sym_packed_len(int64_t K) { return K > 0 ? K * (K + 1) / 2 : 0; }
