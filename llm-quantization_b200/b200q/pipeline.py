@@ -49,7 +49,9 @@ class keep_resident:
         budget = self.max_bytes
         if budget is None and torch.cuda.is_available():
             free, _total = torch.cuda.mem_get_info()
-            budget = int(free * 0.5)          # leave half of what is free now to the kernels' scratch
+            # memory sitting unused in torch's allocator cache is as good as free
+            free += torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+            budget = int(free * 0.5)          # leave half of it to the kernels' scratch
         _resident, _resident_budget, _resident_bytes = {}, int(budget or 0), 0
         return self
 
