@@ -28,6 +28,7 @@ from b200q import pipeline as _pipeline  # noqa: E402
 from quantization_utils import pseudo_quantize_tensor  # noqa: E402,F401  (re-exported like the reference)
 
 SEARCH_STUB = False
+LOOKAHEAD = 2      # under row sharding: Gram matrices (and their exchanges) started ahead of the search
 # What the search runs on a (high-priority) side stream WHILE the Gram GEMM executes: 0 nothing,
 # 1 the activation statistics + salient-channel selection, 2 also the candidate quantisation (dW_c
 # for every c).  Measured on one B200 (Llama-2-7B shapes, same box, interleaved): the kernels do
@@ -175,8 +176,13 @@ def awq_search_scale_factor(
         i = index[name]
         if name not in grams:
             start_gram(i, W.device)
-        if _dist.is_sharded() and i + 1 < len(items):
-            start_gram(i + 1, W.device)
+        if _dist.is_sharded():
+            # two layers ahead: the exchange of layer i+1 (reduce-scatter, fold, all-gather on the
+            # communication stream) then has the Gram GEMM of layer i+2 AND this layer's search to
+            # hide behind -- at 8 GPUs one search alone (~0.5 ms) is shorter than the exchange
+            for j in range(i + 1, min(i + 1 + LOOKAHEAD, len(items))):
+                if items[j][0] not in grams:
+                    start_gram(j, W.device)
         side = _side_stream(W.device) if SEARCH_OVERLAP >= 1 else main
         side.wait_event(before)
         with torch.cuda.stream(side):

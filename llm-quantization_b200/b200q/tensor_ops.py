@@ -171,7 +171,8 @@ def gptq_compensated(W: torch.Tensor, H: Optional[torch.Tensor], n_bit: int, gro
 
 
 # ---- symmetric matrices between GPUs: the packed lower triangle ---------------------------------
-PACKED_EXCHANGE = True     # False: plain fp32 [K,K] all-reduce (A/B timing, non-NCCL backends)
+# False (or B200Q_PACKED_EXCHANGE=0): plain fp32 [K,K] all-reduce (A/B timing, non-NCCL backends)
+PACKED_EXCHANGE = __import__("os").environ.get("B200Q_PACKED_EXCHANGE", "1") != "0"
 _comm_streams = {}
 
 
