@@ -546,7 +546,15 @@ def main():
     device = torch.device("cuda", local_rank)
     import torch.distributed as td
     if world > 1:
-        td.init_process_group("nccl", device_id=device)
+        # NCCL's kernels on a high-priority stream: the block scheduler then places them ahead of the
+        # thousands of pending GEMM blocks instead of at the GEMM's tail, so an exchange really runs
+        # WHILE the next layer's Gram GEMM does (the quantizers queue exchanges on a side stream)
+        opts = None
+        try:
+            opts = td.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            pass
+        td.init_process_group("nccl", device_id=device, pg_options=opts)
     from b200q import _lib, ops, dist as bdist
 
     layers = layer_list(args.model)

@@ -184,7 +184,8 @@ def comm_stream(device) -> torch.cuda.Stream:
 def _comm_stream(device) -> torch.cuda.Stream:
     s = _comm_streams.get(device.index)
     if s is None:
-        s = _comm_streams[device.index] = torch.cuda.Stream(device)
+        # (high priority: its small pack / fold / unpack kernels must not queue behind a GEMM's grid)
+        s = _comm_streams[device.index] = torch.cuda.Stream(device, priority=-1)
     return s
 
 
