@@ -7,16 +7,18 @@
 // the PACKED weight: 0.5 byte per weight from HBM instead of the 2 bytes of a fake-quantised fp16
 // copy.
 //
-// One CTA per 128 x 128 output tile, 4-stage ring over 64-wide k-blocks:
-//   warp 0      TMA producer: X tile (128 tokens x 64 k) -> swizzled smem            (A, K-major)
-//   warps 4-7   dequant producers: thread r owns weight row n0 + r of the tile; per k-block it
-//               reads the row's 32 bytes of codes, turns them into 64 16-bit weights and writes
+// One CTA per 256 x 128 output tile (two 128-token blocks share every dequantised weight tile),
+// 4-stage ring over 64-wide k-blocks:
+//   warp 0      TMA producer: X tile (256 tokens x 64 k) -> swizzled smem            (A, K-major)
+//   warps 4-11  dequant producers: two threads per weight row n0 + r of the tile; per k-block each
+//               reads 16 of the row's 32 bytes of codes (three k-blocks ahead: the global-load latency of a
+//               row-strided 32-byte read is ~1 us, longer than a stage), turns them into 64 16-bit weights and writes
 //               them into shared memory IN THE 128-BYTE-SWIZZLED K-MAJOR LAYOUT the UMMA
 //               descriptor expects (16-byte chunk c of row r lands at chunk c ^ (r & 7)), then
 //               fence.proxy.async + one mbarrier arrival per warp                    (B, K-major)
-//   warp 1      MMA issuer: tcgen05.mma (128 x 128 x 16, fp32 accumulator in TMEM) once both
-//               halves of a stage are full; tcgen05.commit frees the stage
-//   warps 4-7   epilogue after the last k-block: TMEM -> registers -> Y.
+//   warp 1      MMA issuer: two tcgen05.mma (128 x 128 x 16 each, fp32 accumulators in TMEM) per
+//               k-step once both halves of a stage are full; tcgen05.commit frees the stage
+//   warps 4-11  epilogue after the last k-block: TMEM -> registers -> Y (one 128-token block per warp set).
 // int4 -> fp16/bf16 without I2F: (w >> 4j) & 0x000f000f | magic puts two codes into the mantissas
 // of 1024 + q (fp16) / 128 + q (bf16); q - zero is then one exact HSUB2.  For 16-bit records the
 // product with the 16-bit scale is a single HMUL2 -- bit for bit what export.dequantize computes
@@ -33,13 +35,16 @@ namespace b200q {
 using namespace sm100;
 
 namespace qg {
-constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16, STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2;     // 16 KiB
+constexpr int MB = 2;                    // 128-token blocks per CTA: each dequantised B tile feeds MB MMAs
+constexpr int BM = 128 * MB, BN = 128, BK = 64, UMMA_K = 16, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;     // 32 KiB
 constexpr int B_BYTES = BN * BK * 2;     // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-constexpr int THREADS = 256;
-constexpr uint32_t TMEM_COLS = 128;
+constexpr int DQ_PARTS = 2;               // dequant threads per weight row (8 / DQ_PARTS packed words each); measured at 2048x4096x4096: 1 -> 184 us, 2 -> 118 us, 4 -> 172 us
+constexpr int THREADS = 128 + 128 * DQ_PARTS;   // warps 0-3: TMA / MMA / TMEM roles, the rest: dequant + epilogue
+constexpr uint32_t TMEM_COLS = 128 * MB; // MB accumulators of 128 x 128 fp32
+constexpr int PREFETCH = 3;              // k-blocks of packed codes in flight per dequant thread
 }  // namespace qg
 
 template <typename T>
@@ -68,30 +73,43 @@ __device__ __forceinline__ uint32_t as_u32(V2 v) { return *reinterpret_cast<uint
 template <typename V2>
 __device__ __forceinline__ V2 as_v2(uint32_t u) { return *reinterpret_cast<V2*>(&u); }
 
+// Group parameters in the form the inner loop consumes.  The float -> 16-bit conversions run on the
+// quarter-rate XU pipe (ncu on the first version: XU 81 % busy with one conversion pair per packed
+// word), so they are done once per group, not per word.
+template <typename T>
+struct GroupParams {
+  typename Pair16<T>::V2 bias;    // magic + zero point, both halves
+  typename Pair16<T>::V2 scale2;  // the scale as a 16-bit pair (16-bit records)
+  float scale;                    // the scale in fp32 (fp32 records)
+  __device__ __forceinline__ void set(float s, float z) {
+    bias = Pair16<T>::bias(z);
+    scale2 = Pair16<T>::from_float(s);
+    scale = s;
+  }
+};
+
 // eight 4-bit codes of one packed word -> eight 16-bit weights (four packed pairs, element order)
 template <typename T, bool REC_F32>
-__device__ __forceinline__ void dequant_word(uint32_t w, float scale, float zero, uint32_t (&out)[4]) {
+__device__ __forceinline__ void dequant_word(uint32_t w, const GroupParams<T>& gp, uint32_t (&out)[4]) {
   using P = Pair16<T>;
   using V2 = typename P::V2;
-  const V2 bias = P::bias(zero);                 // 1024 + z (exact: z is an integer <= 15)
   V2 h[4];                                       // h[j] = (code j, code j + 4) - z
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const uint32_t bits = ((w >> (4 * j)) & 0x000f000fu) | P::MAGIC;
-    h[j] = __hsub2(as_v2<V2>(bits), bias);
+    h[j] = __hsub2(as_v2<V2>(bits), gp.bias);    // exact: integers below 2048 (fp16) / 256 (bf16)
   }
   if constexpr (REC_F32) {
     // fp32 record: (q - z) * s in fp32, one rounding to the activation dtype
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = P::to_float2(h[j]);
-      h[j] = P::from_float2(f.x * scale, f.y * scale);
+      h[j] = P::from_float2(f.x * gp.scale, f.y * gp.scale);
     }
   } else {
     // 16-bit record: the scale IS a value of that dtype; (q - z) * s rounded to it (export.dequantize)
-    const V2 s2 = P::from_float(scale);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = __hmul2(h[j], s2);
+    for (int j = 0; j < 4; ++j) h[j] = __hmul2(h[j], gp.scale2);
   }
   // (c0,c4) (c1,c5) (c2,c6) (c3,c7)  ->  (c0,c1) (c2,c3) (c4,c5) (c6,c7)
   out[0] = __byte_perm(as_u32(h[0]), as_u32(h[1]), 0x5410);
@@ -125,7 +143,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __
     tma_prefetch_desc(&tmap_x);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_a[s], 1);
-      mbar_init(&full_b[s], 4);                   // one arrival per dequant warp
+      mbar_init(&full_b[s], 4 * DQ_PARTS);        // one arrival per dequant warp
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(acc_full, 1);
@@ -150,7 +168,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN, kBf16, /*a_mn=*/false, /*b_mn=*/false);
+      constexpr uint32_t idesc = make_idesc_f16(128, BN, kBf16, /*a_mn=*/false, /*b_mn=*/false);
       int stage = 0; uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_a[stage], phase);
@@ -160,9 +178,12 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __
         const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t da = make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
-          mma_f16_ss(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + mb * (128 * BK * 2) + k * UMMA_K * 2, 16, 1024);
+            mma_f16_ss(tmem_base + (uint32_t)(mb * 128), da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
         }
         mma_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -170,8 +191,11 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __
       mma_commit(acc_full);
     }
   } else if (warp >= 4) {
-    // ===== dequant producers: thread r <-> weight row n0 + r =====
-    const int r = (warp - 4) * 32 + lane;
+    // ===== dequant producers: DQ_PARTS threads per weight row n0 + r, WPT packed words each =====
+    constexpr int WPT = 8 / DQ_PARTS;
+    const int dq = warp - 4;
+    const int r = (dq & 3) * 32 + lane;
+    const int half = dq >> 2;                      // words [WPT * half, WPT * half + WPT) of the k-block
     const int64_t n = n0 + r;
     const bool row_ok = n < N;
     const uint32_t* qrow = qweight + (row_ok ? n : 0) * words_per_row;
@@ -179,77 +203,116 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __
     const float* zrow = zeros + (row_ok ? n : 0) * groups_per_row;
     int stage = 0; uint32_t phase = 0;
     int64_t cur_g = -1;
-    float sc = 0.f, zp = 0.f;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      // this row's 8 words of the k-block (two 16-byte loads), fetched before the stage is free
-      uint32_t w[8];
-      const int64_t w0 = (int64_t)kb * (BK / 8);
+    GroupParams<T> gp;
+    gp.set(0.f, 0.f);
+    // this thread's 4 words of a k-block (one 16-byte load), fetched PREFETCH k-blocks ahead together
+    // with the group parameters of the k-block's first group: for group sizes that are multiples of
+    // 64 -- every k-block inside one group -- nothing else is loaded in the dequant loop
+    auto load_words = [&](int kb, uint32_t (&w)[WPT], float& s_pre, float& z_pre) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = 0u;
-      if (row_ok) {
-        if (w0 + 8 <= words_per_row) {
+      for (int i = 0; i < WPT; ++i) w[i] = 0u;
+      const int64_t w0 = (int64_t)kb * (BK / 8) + WPT * half;
+      if (!row_ok || kb >= num_kb) return;
+      const int64_t g0 = ((int64_t)kb * BK) / G;
+      s_pre = __ldg(srow + g0);
+      z_pre = __ldg(zrow + g0);
+      if (w0 + WPT <= words_per_row) {
+        if constexpr (WPT == 4) {
           const uint4 a = __ldg(reinterpret_cast<const uint4*>(qrow + w0));
-          const uint4 b = __ldg(reinterpret_cast<const uint4*>(qrow + w0 + 4));
-          w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+          w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+        } else if constexpr (WPT == 2) {
+          const uint2 a = __ldg(reinterpret_cast<const uint2*>(qrow + w0));
+          w[0] = a.x; w[1] = a.y;
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (w0 + i < words_per_row) w[i] = __ldg(qrow + w0 + i);
+          for (int i = 0; i < WPT; ++i) w[i] = __ldg(qrow + w0 + i);
         }
-      }
-      mbar_wait(&empty_bar[stage], phase ^ 1);
-      uint8_t* brow = smem + stage * STAGE_BYTES + A_BYTES + r * 128;
+      } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t k = (int64_t)kb * BK + i * 8;
-        uint32_t o[4] = {0u, 0u, 0u, 0u};
-        if (row_ok && k < K) {
-          const int64_t g = k / G;
-          if (g != cur_g) { cur_g = g; sc = __ldg(srow + g); zp = __ldg(zrow + g); }
-          dequant_word<T, REC_F32>(w[i], sc, zp, o);
-        }
-        // 128-byte swizzle: 16-byte chunk i of row r sits at chunk i ^ (r & 7)
-        *reinterpret_cast<uint4*>(brow + ((i ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int i = 0; i < WPT; ++i)
+          if (w0 + i < words_per_row) w[i] = __ldg(qrow + w0 + i);
       }
-      fence_proxy_async_smem();                     // generic-proxy writes -> visible to the MMA
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_b[stage]);
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    };
+    uint32_t wq[PREFETCH][WPT];
+    float sq[PREFETCH], zq[PREFETCH];
+#pragma unroll
+    for (int p = 0; p < PREFETCH; ++p) { sq[p] = 0.f; zq[p] = 0.f; load_words(p, wq[p], sq[p], zq[p]); }
+    const bool one_group_per_block = (G % BK) == 0;
+    for (int kb0 = 0; kb0 < num_kb; kb0 += PREFETCH) {
+#pragma unroll
+      for (int p = 0; p < PREFETCH; ++p) {
+        const int kb = kb0 + p;
+        if (kb < num_kb) {                 // (a predicate, not a break: the slots stay in registers)
+        uint32_t w[WPT];
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) w[i] = wq[p][i];
+        if (one_group_per_block) gp.set(sq[p], zq[p]);
+        load_words(kb + PREFETCH, wq[p], sq[p], zq[p]);   // refill this slot for PREFETCH k-blocks ahead
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* brow = smem + stage * STAGE_BYTES + A_BYTES + r * 128;
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+          const int c = WPT * half + i;             // 16-byte chunk (8 weights) of the row
+          const int64_t k = (int64_t)kb * BK + c * 8;
+          uint32_t o[4] = {0u, 0u, 0u, 0u};
+          if (row_ok && k < K) {
+            if (!one_group_per_block) {                 // small groups: several per k-block
+              const int64_t g = k / G;
+              if (g != cur_g) { cur_g = g; gp.set(__ldg(srow + g), __ldg(zrow + g)); }
+            }
+            dequant_word<T, REC_F32>(w[i], gp, o);
+          }
+          // 128-byte swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+          *reinterpret_cast<uint4*>(brow + ((c ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        fence_proxy_async_smem();                     // generic-proxy writes -> visible to the MMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_b[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
     }
     // ===== epilogue =====
     const int q = warp & 3;
-    const int64_t row = m0 + q * 32 + lane;
     mbar_wait(acc_full, 0);
     tc_fence_after_sync();
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(lane_base + (uint32_t)(c * 32), v);
-      tmem_ld_wait();
-      const int64_t col0 = n0 + c * 32;
-      if (row >= M || col0 >= N) continue;
-      if constexpr (OUT_F32) {
-        float* dst = static_cast<float*>(Y) + row * N + col0;
-        if (col0 + 32 <= N && (N % 4 == 0)) {
+    for (int mb = half; mb < MB; mb += DQ_PARTS) {   // one 128-token block per set of four warps
+      const int64_t row = m0 + mb * 128 + q * 32 + lane;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * 128);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(lane_base + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        const int64_t col0 = n0 + c * 32;
+        if (row >= M || col0 >= N) continue;
+        if constexpr (OUT_F32) {
+          float* dst = static_cast<float*>(Y) + row * N + col0;
+          if (col0 + 32 <= N && (N % 4 == 0)) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<uint4*>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < 32 && col0 + j < N; ++j) dst[j] = __uint_as_float(v[j]);
-        }
-      } else {
-        T* dst = static_cast<T*>(Y) + row * N + col0;
-        if (col0 + 32 <= N && (N % 8 == 0)) {
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4*>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float f[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) f[u] = __uint_as_float(v[j + u]);
-            *reinterpret_cast<uint4*>(dst + j) = pack16<T>(f);
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) dst[j] = __uint_as_float(v[j]);
           }
         } else {
-          for (int j = 0; j < 32 && col0 + j < N; ++j) dst[j] = from_f<T>(__uint_as_float(v[j]));
+          T* dst = static_cast<T*>(Y) + row * N + col0;
+          if (col0 + 32 <= N && (N % 8 == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float f[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) f[u] = __uint_as_float(v[j + u]);
+              *reinterpret_cast<uint4*>(dst + j) = pack16<T>(f);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) dst[j] = from_f<T>(__uint_as_float(v[j]));
+          }
         }
       }
     }
