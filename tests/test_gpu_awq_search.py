@@ -218,3 +218,30 @@ def test_packed_triangle_exchange_kernels(K):
         a = T.awq_search_losses(W, H, mask, 4, G, cands)
         b = T.awq_search_losses(W, T.FoldedGram(Hb), mask, 4, G, cands)
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,K,n_hot", [(200, 512, 5), (128, 1024, 40), (64, 256, 0), (96, 384, 384)])
+def test_candidate_deltas_equal_the_production_quantizer(dtype, N, K, n_hot):
+    """Stage 1 of the search (dW_c = Q_c(W) - W for every candidate) against the kernel that
+    awq_quantize_model_weight itself uses (group_fakequant with the scale-up / scale-down column
+    op): bit-identical bf16 deltas for every candidate -- including the candidates for which the
+    delta kernel REUSES the previous candidate's non-salient deltas because the group's scale and
+    zero point did not move, groups without any salient column, and the all-salient corner."""
+    from b200q import ops, tensor_ops as T
+    g = torch.Generator().manual_seed(N + K + n_hot)
+    W = (torch.randn(N, K, generator=g) * 0.02).to(dtype).cuda()
+    mask = torch.zeros(K, dtype=torch.uint8)
+    if n_hot:
+        mask[torch.randperm(K, generator=g)[:n_hot]] = 1
+    cands = torch.linspace(1.0, 2.0, 20, dtype=torch.float64).tolist()
+    p = T.awq_search_prepare(W, mask.cuda(), 4, 128, cands)
+    rows_pad = (N + 127) // 128 * 128
+    D = p.work[: len(cands) * rows_pad * K * 2].view(torch.bfloat16).view(len(cands), rows_pad, K)
+    for c, sf in enumerate(cands):
+        colvec = torch.where(mask.bool(), torch.tensor(float(sf)), torch.tensor(1.0)).float().cuda()
+        out = ops.group_fakequant(W, 4, 128, colop=ops.COLOP_MUL_DIV, colvec=colvec)
+        want = (out.float() - W.float()).to(torch.bfloat16)
+        assert torch.equal(D[c, :N], want), (c, sf)
+    if rows_pad != N:
+        assert torch.count_nonzero(D[:, N:]).item() == 0
