@@ -222,15 +222,6 @@ int64_t b200q_hessian_workspace(int64_t T, int64_t K, int n_samples);
 int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, int64_t K, int dtype,
                         int normalize, float* H, int accumulate, float* norms_out, void* work,
                         void* stream);
-/* The plain Gram matrix (normalize = 0) of 16-bit activations WITH the AWQ statistic as a
- * by-product: abs_sum[s, k] = sum over the rows of sample s of |X[., k]| (fp32 [n_samples, K];
- * ref: quantization_utils.py:231 is abs_sum / rows_per_sample), accumulated by the idle warps of the
- * diagonal tiles of the GEMM from its shared-memory stages, so X is read from HBM once instead of
- * twice.  Needs samples of whole 64-row blocks; returns B200Q_EUNSUPPORTED (nothing launched)
- * otherwise -- the caller then uses b200q_act_meanabs_batched. */
-int b200q_hessian_accum_stats(const void* X, int n_samples, int64_t rows_per_sample, int64_t K,
-                              int dtype, float* H, int accumulate, float* abs_sum, void* work,
-                              void* stream);
 /* H = H * scale + damp * I     ref: gptq_quantizer.py:150 (scale = 1/len(input_feat), damp =
  * perp_damp) and :160 (scale = 1, damp = 1e-6) */
 int b200q_hessian_finalize(float* H, int64_t K, float scale, float damp, void* stream);

@@ -29,8 +29,13 @@ from quantization_utils import pseudo_quantize_tensor  # noqa: E402,F401  (re-ex
 
 SEARCH_STUB = False
 LOOKAHEAD = 2      # under row sharding: Gram matrices (and their exchanges) started ahead of the search
-# per-batch mean|x| rows as a by-product of the Gram GEMM (False: always the separate act_meanabs pass)
-FUSED_STATS = __import__("os").environ.get("B200Q_AWQ_FUSED_STATS", "1") != "0"
+# What the search runs on a (high-priority) side stream WHILE the Gram GEMM executes: 0 nothing,
+# 1 the activation statistics + salient-channel selection, 2 also the candidate quantisation (dW_c
+# for every c).  Measured on one B200 (Llama-2-7B shapes, same box, interleaved): the kernels do
+# overlap (statistics 111 -> 221 ms, candidates 205 -> 252 ms elapsed) but the GEMM stretches from
+# 1.55 s to 1.93 s -- the step sits on the 1 kW power cap, so concurrent work just lowers the clock
+# -- and the step does not get shorter (2.60 s vs 2.63 s).  Hence off by default.
+SEARCH_OVERLAP = int(__import__("os").environ.get("B200Q_AWQ_OVERLAP", "0"))
 
 
 def _feat_matrix(feats, device) -> torch.Tensor:
@@ -65,6 +70,18 @@ def _stat_rows(feats: List[torch.Tensor], device) -> torch.Tensor:
         else:
             rows.append(_ops.act_meanabs(_ops.to_device(f)).to(f.dtype))
     return torch.stack(rows)
+
+
+_side_streams = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    s = _side_streams.get(device.index)
+    if s is None:
+        # high priority: the block scheduler hands SM slots to this stream's (small) kernels ahead
+        # of the thousands of pending GEMM blocks, otherwise they would only start at the GEMM's tail
+        s = _side_streams[device.index] = torch.cuda.Stream(device, priority=-1)
+    return s
 
 
 def _importance(feats, device) -> torch.Tensor:
@@ -137,8 +154,7 @@ def awq_search_scale_factor(
     def start_gram(i, device):
         n, m = items[i]
         if supported(m.weight.shape[1]):
-            grams[n] = _tops.gram_matrix_begin(input_feat[n], m.weight.shape[1], device, want_folded=True,
-                                               want_stats=FUSED_STATS)
+            grams[n] = _tops.gram_matrix_begin(input_feat[n], m.weight.shape[1], device, want_folded=True)
 
     skipped = []
 
@@ -150,38 +166,55 @@ def awq_search_scale_factor(
         if not supported(K):
             skipped.append(name)
             return None
-        # The Gram GEMM of this layer is queued first (under row sharding also those of the next
-        # LOOKAHEAD layers: the exchange of layer i+1 -- reduce-scatter, fold, all-gather on the
-        # communication stream -- then has the Gram GEMM of layer i+2 AND this layer's search to hide
-        # behind; at 8 GPUs one search alone, ~0.5 ms, is shorter than the exchange).
+        # The Gram GEMM of this layer (and, under row sharding, of the NEXT one, whose exchange then
+        # hides behind this layer's search) is queued first; with SEARCH_OVERLAP the per-batch
+        # mean|x| statistics, the salient-channel selection and the candidate quantisation run on a
+        # side stream while it executes (see SEARCH_OVERLAP for why that is not the default).
+        main = torch.cuda.current_stream(W.device)
+        before = torch.cuda.Event()
+        before.record(main)
         i = index[name]
         if name not in grams:
             start_gram(i, W.device)
         if _dist.is_sharded():
+            # two layers ahead: the exchange of layer i+1 (reduce-scatter, fold, all-gather on the
+            # communication stream) then has the Gram GEMM of layer i+2 AND this layer's search to
+            # hide behind -- at 8 GPUs one search alone (~0.5 ms) is shorter than the exchange
             for j in range(i + 1, min(i + 1 + LOOKAHEAD, len(items))):
                 if items[j][0] not in grams:
                     start_gram(j, W.device)
-        gram = grams.pop(name)
-        H = _tops.gram_matrix_end(gram, normalise=False)
-        # The statistic the quantizer ranks channels by is the per-batch mean|x|
-        # (quantization_utils.py:231).  For raw 16-bit activations the Gram GEMM has just produced
-        # it as a by-product (X is read from HBM once); 1-D features already are it; anything else
-        # goes through the act_meanabs kernel.
-        from b200q.streaming import ActivationStream
-        if gram.stat_rows is not None:
-            dt = feats.dtype if isinstance(feats, torch.Tensor) else feats[0].dtype
-            stat_rows = gram.stat_rows.to(dt)          # the hook's mean is a value of x's dtype
-        elif isinstance(feats, ActivationStream) or (isinstance(feats, torch.Tensor) and feats.dim() == 2):
-            stat_rows = feats
-        else:
-            stat_rows = _stat_rows(feats, W.device)
-        n_protect = max(1, int(K * protect_ratio))
-        mask = _ops.salient_mask(_feat_matrix(stat_rows, W.device), n_protect)
+        side = _side_stream(W.device) if SEARCH_OVERLAP >= 1 else main
+        side.wait_event(before)
+        with torch.cuda.stream(side):
+            # 2-D [tokens, K] features are raw activations: their per-batch mean|x| is the statistic
+            # the quantizer ranks channels by (quantization_utils.py:231); 1-D features already are it
+            from b200q.streaming import ActivationStream
+            if isinstance(feats, ActivationStream) or (isinstance(feats, torch.Tensor) and feats.dim() == 2):
+                stat_rows = feats
+            else:
+                stat_rows = _stat_rows(feats, W.device)
+            n_protect = max(1, int(K * protect_ratio))
+            mask = _ops.salient_mask(_feat_matrix(stat_rows, W.device), n_protect)
+            # ... and so does the candidate quantisation (dW_c = Q_c(W) - W for every candidate): it
+            # needs W and the mask only and is FP32-issue bound, i.e. it uses what the GEMM leaves idle
+            prepared = None
+            if len(candidates) <= 32 and SEARCH_OVERLAP >= 2:
+                W.record_stream(side)
+                prepared = _tops.awq_search_prepare(W, mask, w_bit, q_group_size, candidates)
+            selected = torch.cuda.Event()
+            selected.record(side)
+        mask.record_stream(main)
+        main.wait_event(selected)
         # the loss is linear in H: search in the plain sum X^T X and divide the n_grid losses by
         # the row count instead of rescaling the [K, K] matrix
-        # (the kernel takes up to 32 candidates per call: longer grids go in slices)
-        loss = torch.cat([_tops.awq_search_losses(W, H, mask, w_bit, q_group_size, candidates[c:c + 32])
-                          for c in range(0, len(candidates), 32)])
+        gram = grams.pop(name)
+        H = _tops.gram_matrix_end(gram, normalise=False)
+        if prepared is not None:
+            loss = _tops.awq_search_finish(prepared, H)
+        else:
+            # (the kernel takes up to 32 candidates per call: longer grids go in slices)
+            loss = torch.cat([_tops.awq_search_losses(W, H, mask, w_bit, q_group_size, candidates[c:c + 32])
+                              for c in range(0, len(candidates), 32)])
         loss.mul_(1.0 / gram.rows_total)
         if totals:
             totals[0] += loss

@@ -61,8 +61,6 @@ SIGNATURES = {
     "b200q_hessian_workspace": (c_i64, [c_i64, c_i64, C.c_int]),
     "b200q_hessian_accum": (C.c_int, [c_vp, C.c_int, c_i64, c_i64, C.c_int, C.c_int, c_fp, C.c_int,
                                       c_fp, c_vp, c_vp]),
-    "b200q_hessian_accum_stats": (C.c_int, [c_vp, C.c_int, c_i64, c_i64, C.c_int, c_fp, C.c_int, c_fp,
-                                            c_vp, c_vp]),
     "b200q_awq_search_workspace": (c_i64, [c_i64, c_i64, C.c_int]),
     "b200q_awq_search_loss": (C.c_int, [c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp,
                                         C.POINTER(C.c_float), C.c_int, c_fp, C.c_int, c_vp, c_fp,

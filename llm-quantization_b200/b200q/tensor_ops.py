@@ -53,34 +53,6 @@ def hessian_accum(X: torch.Tensor, rows_per_sample: int, H: Optional[torch.Tenso
     return (H, norms) if return_norms else H
 
 
-def hessian_accum_stats(X: torch.Tensor, rows_per_sample: int, H: Optional[torch.Tensor] = None):
-    """Plain Gram matrix H (+)= X^T X of a CUDA 16-bit [T, K] matrix together with the per-sample
-    column sums of |x| that the GEMM's idle warps collect from its shared-memory stages: returns
-    (H, abs_sum fp32 [T / rows_per_sample, K]), or None when the kernel cannot provide the
-    by-product for this input (fp32 activations, samples that are not whole 64-row blocks, the
-    one-CTA kernel selected) -- the caller then computes the statistic with act_meanabs_batched."""
-    assert X.is_cuda and X.dim() == 2
-    if X.dtype not in (torch.float16, torch.bfloat16) or rows_per_sample % 64 != 0:
-        return None
-    X = X.contiguous()
-    T, K = X.shape
-    assert T % rows_per_sample == 0
-    n = T // rows_per_sample
-    accumulate = H is not None
-    Hout = H if accumulate else torch.empty((K, K), dtype=torch.float32, device=X.device)
-    sums = torch.empty((n, K), dtype=torch.float32, device=X.device)
-    lib = _lib.load()
-    with _on(X.device):
-        work = _workspace(X.device, lib.b200q_hessian_workspace(T, K, n))
-        rc = lib.b200q_hessian_accum_stats(X.data_ptr(), n, rows_per_sample, K, dtype_code(X),
-                                           Hout.data_ptr(), int(accumulate), sums.data_ptr(),
-                                           work.data_ptr(), _stream())
-    if rc == -3:
-        return None
-    _lib.check(rc, "hessian_accum_stats")
-    return Hout, sums
-
-
 def hessian_finalize(H: torch.Tensor, scale: float, damp: float) -> torch.Tensor:
     with _on(H.device):
         rc = _lib.load().b200q_hessian_finalize(H.data_ptr(), H.shape[0], float(scale), float(damp),
@@ -261,12 +233,11 @@ class FoldedGram:
 
 class PendingGram:
     """A Gram matrix whose cross-rank sum may still be in flight (see gram_matrix_begin)."""
-    __slots__ = ("H", "work", "rows_total", "folded", "event", "nbytes", "stat_rows")
+    __slots__ = ("H", "work", "rows_total", "folded", "event", "nbytes")
 
     def __init__(self, H, work, rows_total, folded=None, event=None, nbytes=0):
         self.H, self.work, self.rows_total = H, work, rows_total
         self.folded, self.event, self.nbytes = folded, event, nbytes
-        self.stat_rows = None     # fp32 [n_batches, K] per-batch mean|x| rows, when the GEMM produced them
 
 
 def _exchange_folded(H: torch.Tensor) -> PendingGram:
@@ -304,33 +275,14 @@ def _exchange_folded(H: torch.Tensor) -> PendingGram:
     return PendingGram(None, None, 0, folded=FoldedGram(Hb), event=ev, nbytes=Lp * 4 + Lp * 2)
 
 
-def _batch_rows(input_feat, K: int) -> Optional[int]:
-    """Rows per calibration batch when the features are raw activations in equal batches
-    ([n, rows, K] tensor or a list of [rows, K] tensors), else None."""
-    if isinstance(input_feat, torch.Tensor):
-        return int(input_feat.shape[1]) if input_feat.dim() == 3 else None
-    rows = None
-    for f in input_feat:
-        if not isinstance(f, torch.Tensor) or f.dim() < 2:
-            return None
-        r = f.numel() // K
-        if rows is not None and r != rows:
-            return None
-        rows = r
-    return rows
-
-
 def gram_matrix_begin(input_feat: Sequence, in_features: int, device,
-                      want_folded: bool = False, want_stats: bool = False) -> PendingGram:
+                      want_folded: bool = False) -> PendingGram:
     """Launch X^T X over this rank's share of the calibration rows and, under row sharding, START
     the all-reduce of the partial sums without waiting for it: the caller can queue the next
     layer's kernels behind this one and pick the result up later with gram_matrix_end.
     want_folded: the caller is the AWQ search, which only needs the matrix folded onto its lower
     triangle in bf16 -- under sharding the exchange then runs packed (see _exchange_folded) and
-    gram_matrix_end returns a FoldedGram.
-    want_stats: also produce the per-batch mean|x| rows (the AWQ statistic) as a by-product of the
-    GEMM when the input allows it (16-bit activations in equal batches of whole 64-row blocks):
-    `stat_rows` of the result, valid after gram_matrix_end; None when the caller has to compute them."""
+    gram_matrix_end returns a FoldedGram."""
     device = torch.device(device)
     K = in_features
     from .streaming import ActivationStream
@@ -338,7 +290,6 @@ def gram_matrix_begin(input_feat: Sequence, in_features: int, device,
         assert not input_feat.normalize and input_feat.in_features == K
         H = input_feat.matrix_sum(device)            # (already all-reduced: nothing left in flight)
         return PendingGram(H, None, max(1, input_feat.total_rows(device)))
-    batch_rows = _batch_rows(input_feat, K) if want_stats else None
     if isinstance(input_feat, torch.Tensor):
         X = input_feat.reshape(-1, K)
     else:
@@ -347,55 +298,26 @@ def gram_matrix_begin(input_feat: Sequence, in_features: int, device,
     if X.dtype not in DTYPE_CODE:
         X = X.float()
     rows_total = X.shape[0]
-    with_stats = (batch_rows is not None and batch_rows % 64 == 0 and
-                  X.dtype in (torch.float16, torch.bfloat16))
-    if with_stats:
-        rows = batch_rows                            # shards and statistics follow the real batches
-    else:
-        # samples only matter for the fp16 pre-scaling of fp32 input here; use runs of up to 2048 rows
-        rows = 1
-        for cand in (2048, 1024, 512, 256, 128, 64, 32, 16, 8, 4, 2):
-            if rows_total % cand == 0:
-                rows = cand
-                break
-    n = rows_total // rows
-    world, rank = _dist.world_size(), _dist.rank()
-    if _dist.is_sharded() and with_stats and n % world != 0:
-        with_stats = False                           # unequal shares: the rows could not be all-gathered
-    lo, hi = _dist.shard_rows(n, world, rank) if _dist.is_sharded() else (0, n)
-
-    def accumulate(Xs):
-        """(H, per-batch |x| sums or None) over this rank's rows."""
-        if with_stats:
-            res = hessian_accum_stats(Xs, rows)
-            if res is not None:
-                return res
-        return hessian_accum(Xs, rows, normalize=False), None
-
-    if hi > lo:
-        H, sums = accumulate(X[lo * rows:hi * rows])
-    else:
-        H, sums = torch.zeros((K, K), dtype=torch.float32, device=device), None
-    stat_rows = None
-    if sums is not None:
-        stat_rows = sums.mul_(1.0 / rows)            # mean over the batch's rows, fp32
+    # samples only matter for the fp16 pre-scaling of fp32 input here; use runs of up to 2048 rows
+    rows = 1
+    for cand in (2048, 1024, 512, 256, 128, 64, 32, 16, 8, 4, 2):
+        if rows_total % cand == 0:
+            rows = cand
+            break
+    work = None
     if _dist.is_sharded():
-        if stat_rows is not None:
-            # every rank needs every batch's row: all-gather the [n / world, K] shares (whether the
-            # kernel provides the by-product depends on dtype, batch size and environment only, so
-            # all ranks take this branch together)
-            mine = stat_rows.contiguous()
-            stat_rows = torch.empty((n, K), dtype=torch.float32, device=device)
-            _dist.all_gather_into(stat_rows, mine)
+        n = rows_total // rows
+        lo, hi = _dist.shard_rows(n, _dist.world_size(), _dist.rank())
+        H = hessian_accum(X[lo * rows:hi * rows], rows, normalize=False) if hi > lo else \
+            torch.zeros((K, K), dtype=torch.float32, device=device)
         if want_folded and PACKED_EXCHANGE and _dist.backend_is_nccl():
             p = _exchange_folded(H)
             p.rows_total = rows_total
-        else:
-            p = PendingGram(H, _dist.allreduce_sum_async(H), rows_total)
+            return p
+        work = _dist.allreduce_sum_async(H)
     else:
-        p = PendingGram(H, None, rows_total)
-    p.stat_rows = stat_rows
-    return p
+        H = hessian_accum(X, rows, normalize=False)
+    return PendingGram(H, work, rows_total)
 
 
 def gram_matrix_end(p: PendingGram, normalise: bool = True) -> torch.Tensor:

@@ -431,8 +431,7 @@ template <bool BF16, bool PER_SAMPLE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(hg2::THREADS, 1)
 hessian_gemm2_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ partial,
                      int64_t K, int64_t T, int64_t tokens_per_split, int tiles_n,
-                     const float* __restrict__ norms, int kb_per_sample, int raster_m,
-                     float* __restrict__ abs_sum, int kb_per_stat_sample) {
+                     const float* __restrict__ norms, int kb_per_sample, int raster_m) {
   using namespace hg2;
   const int RASTER_M = raster_m;
   constexpr uint32_t kTmemCols = PER_SAMPLE ? 512u : 256u;
@@ -443,8 +442,7 @@ hessian_gemm2_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict
   uint64_t* empty_bar = full_bar + STAGES;             // one per CTA, fed by the multicast commit
   uint64_t* tmem_full_bar = empty_bar + STAGES;        // one per CTA, fed by the multicast commit
   uint64_t* chunk_free_bar = tmem_full_bar + 1;        // leader: 8 epilogue warps (4 per CTA)
-  uint64_t* ready_bar = chunk_free_bar + 1;            // peer: "your stage is full" relayed by the leader
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready_bar + STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(chunk_free_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -460,11 +458,6 @@ hessian_gemm2_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict
   const int z = blockIdx.y;
   // tiles entirely below the diagonal do not run (both CTAs of the pair take the same decision)
   if (n_blk < m_blk) return;
-  // Per-sample sum of |x| per channel as a by-product (the AWQ statistic, quantization_utils.py:231):
-  // on DIAGONAL tiles this CTA's A operand is channels [m0 + 128 rank, +128) of every token, each
-  // channel exactly once over all diagonal tiles -- the two otherwise idle warps add them up from the
-  // shared-memory stages, which saves the separate pass that reads X from HBM a second time.
-  const bool stats = abs_sum != nullptr && n_blk == m_blk;
   const int64_t t0 = (int64_t)z * tokens_per_split;
   const int64_t t1 = min(T, t0 + tokens_per_split);
   const int num_kb = (int)((t1 - t0 + BKT - 1) / BKT);
@@ -476,8 +469,7 @@ hessian_gemm2_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict
     tma_prefetch_desc(&tmap);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], stats ? 3u : 1u);     // the MMA commit (+ the two statistics warps)
-      mbar_init(&ready_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
     mbar_init(chunk_free_bar, 8);
@@ -542,54 +534,6 @@ hessian_gemm2_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         mma_commit_pair(tmem_full_bar);           // (chunk) accumulator complete, both CTAs
-      }
-    }
-  } else if ((warp == 2 || warp == 3) && stats) {
-    // ===== warps 2, 3: |x| column sums of this CTA's A tile (diagonal tiles only) =====
-    const int t = (warp - 2) * 32 + lane;            // channel pair 2t, 2t+1 of the 128 A channels
-    const uint32_t box_off = (uint32_t)(t >> 5) * BOX_BYTES;
-    const uint32_t chunk = (uint32_t)(t & 31) >> 2, within = ((uint32_t)(t & 31) & 3u) * 4u;
-    const int64_t ch = (int64_t)m_blk * BM + (int64_t)rank * 128 + 2 * t;
-    const uint32_t peer_ready0 = mapa_u32(smem_u32(&ready_bar[0]), 1);
-    float acc0 = 0.f, acc1 = 0.f;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      if (leader) {
-        mbar_wait(&full_bar[stage], phase);          // both CTAs' loads of this stage have landed
-        if (warp == 2 && lane == 0) mbar_arrive_cluster(peer_ready0 + (uint32_t)stage * 8u);
-      } else {
-        mbar_wait(&ready_bar[stage], phase);
-      }
-      const uint8_t* a = smem + stage * STAGE_BYTES + box_off;
-#pragma unroll 8
-      for (int tau = 0; tau < BKT; ++tau) {
-        // MN-major box: token row tau = 128 bytes, 16-byte chunk c stored at c ^ (tau & 7)
-        const uint32_t u = *reinterpret_cast<const uint32_t*>(
-            a + tau * 128 + ((chunk ^ ((uint32_t)tau & 7u)) << 4) + within);
-        float x0, x1;
-        if constexpr (BF16) {
-          x0 = __uint_as_float(u << 16);
-          x1 = __uint_as_float(u & 0xffff0000u);
-        } else {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
-          x0 = f.x; x1 = f.y;
-        }
-        acc0 += fabsf(x0);
-        acc1 += fabsf(x1);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[stage]);
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      // end of a calibration sample (or of this split's token range): hand the partial sums over.
-      // A (sample, channel) gets at most two contributions (a sample straddles at most one split
-      // boundary), added to a zeroed buffer: the result does not depend on their order.
-      const int64_t kb_abs = t0 / BKT + kb;
-      if ((kb_abs + 1) % kb_per_stat_sample == 0 || kb == num_kb - 1) {
-        const int64_t sample = kb_abs / kb_per_stat_sample;
-        if (ch < K) atomicAdd(abs_sum + sample * K + ch, acc0);
-        if (ch + 1 < K) atomicAdd(abs_sum + sample * K + ch + 1, acc1);
-        acc0 = acc1 = 0.f;
       }
     }
   } else if (warp >= 4) {
@@ -1201,9 +1145,9 @@ int64_t b200q_hessian_workspace(int64_t T, int64_t K, int n_samples) {
   return hessian_layout(nullptr, T, K, n_samples, -1).bytes;
 }
 
-static int hessian_accum_impl(const void* X, int n_samples, int64_t rows_per_sample, int64_t K, int dtype,
-                              int normalize, float* H, int accumulate, float* norms_out, void* work,
-                              float* abs_sum, void* stream) {
+int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, int64_t K, int dtype,
+                        int normalize, float* H, int accumulate, float* norms_out, void* work,
+                        void* stream) {
   B200Q_REQUIRE(X && H && work, "hessian_accum: null pointer");
   B200Q_REQUIRE(n_samples > 0 && rows_per_sample > 0 && K > 0, "hessian_accum: bad shape");
   B200Q_REQUIRE(K % 8 == 0, "hessian_accum: in_features must be a multiple of 8");
@@ -1226,13 +1170,6 @@ static int hessian_accum_impl(const void* X, int n_samples, int64_t rows_per_sam
                           rows_per_sample >= 8 * hg::BKT;
   const bool in_place = direct || per_sample;
   const bool bf16_ops = in_place && dtype == B200Q_BF16;
-  if (abs_sum != nullptr) {
-    // the |x| by-product exists in the CTA-pair kernel reading 16-bit activations in place
-    if (!(direct && hessian_pair() && rows_per_sample % hg2::BKT == 0))
-      return fail(B200Q_EUNSUPPORTED, "hessian_accum_stats: needs 16-bit activations, normalize = 0, "
-                                      "samples of whole 64-token blocks and the CTA-pair kernel");
-    cudaMemsetAsync(abs_sum, 0, sizeof(float) * (size_t)n_samples * K, st);
-  }
   HessianWork w = hessian_layout(work, T, K, n_samples, (direct && !accumulate) ? 1 : 0);
   if (!direct) {
     KernelScope scope("hessian_prescale", (per_sample ? 1.0 : 3.0) * T * K * elem_size(dtype), 0, st);
@@ -1329,8 +1266,7 @@ static int hessian_accum_impl(const void* X, int n_samples, int64_t rows_per_sam
     do {                                                                                          \
       if (pair)                                                                                   \
         hessian_gemm2_kernel<BF, PS><<<grid, hg2::THREADS, hg2::SMEM_BYTES, st>>>(                 \
-            tmap, gemm_out, K, T, tokens_per_split, tiles_n, norms, kb_per_sample, raster_m,      \
-            abs_sum, (int)(rows_per_sample / hg2::BKT));                                          \
+            tmap, gemm_out, K, T, tokens_per_split, tiles_n, norms, kb_per_sample, raster_m);     \
       else                                                                                        \
         hessian_gemm_kernel<BF, PS><<<grid, hg::THREADS, hg::SMEM_BYTES, st>>>(                    \
             tmap, gemm_out, K, T, tokens_per_split, tiles_n, norms, kb_per_sample);               \
@@ -1362,21 +1298,6 @@ static int hessian_accum_impl(const void* X, int n_samples, int64_t rows_per_sam
     rc = check_launch("hessian_reduce");
   }
   return rc;
-}
-
-int b200q_hessian_accum(const void* X, int n_samples, int64_t rows_per_sample, int64_t K, int dtype,
-                        int normalize, float* H, int accumulate, float* norms_out, void* work,
-                        void* stream) {
-  return hessian_accum_impl(X, n_samples, rows_per_sample, K, dtype, normalize, H, accumulate, norms_out,
-                            work, nullptr, stream);
-}
-
-int b200q_hessian_accum_stats(const void* X, int n_samples, int64_t rows_per_sample, int64_t K,
-                              int dtype, float* H, int accumulate, float* abs_sum, void* work,
-                              void* stream) {
-  B200Q_REQUIRE(abs_sum != nullptr, "hessian_accum_stats: null pointer");
-  return hessian_accum_impl(X, n_samples, rows_per_sample, K, dtype, /*normalize=*/0, H, accumulate,
-                            nullptr, work, abs_sum, stream);
 }
 
 int b200q_hessian_finalize(float* H, int64_t K, float scale, float damp, void* stream) {

@@ -245,44 +245,3 @@ def test_candidate_deltas_equal_the_production_quantizer(dtype, N, K, n_hot):
         assert torch.equal(D[c, :N], want), (c, sf)
     if rows_pad != N:
         assert torch.count_nonzero(D[:, N:]).item() == 0
-
-
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("K,n,rows", [(512, 4, 128), (384, 6, 64), (4096, 8, 2048), (1000, 3, 192)])
-def test_gram_gemm_by_product_statistics(dtype, K, n, rows):
-    """The per-batch sum of |x| that the Gram GEMM's idle warps collect on its diagonal tiles
-    (quantization_utils.py:231 is that sum / rows): equal to the act_meanabs kernel's result up to
-    fp32 summation order, for every batch and channel, next to an unchanged Gram matrix -- with
-    token splits (a batch straddling two splits), ragged K (1000) and both 16-bit types."""
-    from b200q import ops, tensor_ops as T
-    g = torch.Generator(device="cuda").manual_seed(K + n)
-    X = (torch.randn(n * rows, K, device="cuda", generator=g) * 3).to(dtype)
-    res = T.hessian_accum_stats(X, rows)
-    assert res is not None
-    H, sums = res
-    want_H = T.hessian_accum(X, rows, normalize=False)
-    assert torch.equal(H, want_H)
-    want = ops.act_meanabs_batched(X.view(n, rows, K))
-    torch.testing.assert_close(sums / rows, want, rtol=2e-6, atol=0)
-    exact = X.view(n, rows, K).double().abs().sum(1)
-    assert ((sums.double() - exact).abs() / exact).max().item() < 1e-6
-    # inputs the kernel cannot serve are declined, not mis-served
-    assert T.hessian_accum_stats(X.float(), rows) is None
-    assert T.hessian_accum_stats(X[: n * 32], 32) is None            # batches of half a 64-row block
-
-
-def test_search_uses_the_by_product_and_matches_the_separate_pass():
-    import awq_quantizer as aq
-    W, feats, hot = setup(256, 512, 7, n=8, rows=128)
-    feats16 = torch.stack(feats).to(torch.bfloat16).cuda()              # [n, rows, K] raw activations
-    net = nn.Sequential(nn.Linear(512, 256, bias=False)).cuda()
-    net[0].weight.data = W.clone().cuda()
-    old = aq.FUSED_STATS
-    try:
-        aq.FUSED_STATS = True
-        a = aq.awq_search_scale_factor(net, 4, 128, {"0": feats16}, n_grid=20)
-        aq.FUSED_STATS = False
-        b = aq.awq_search_scale_factor(net, 4, 128, {"0": feats16}, n_grid=20)
-    finally:
-        aq.FUSED_STATS = old
-    assert a == b
