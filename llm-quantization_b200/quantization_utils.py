@@ -43,7 +43,10 @@ def pseudo_quantize_tensor(w: Tensor, n_bit: int = 4, q_group_size: int = -1) ->
 
     Same contract as the reference (quantization_utils.py:362-413): new tensor, input's shape and
     dtype, AssertionError when the last dim is not divisible by the group size or the tensor is not
-    2-D in per-row mode.  fp32 results are bit-identical to the reference's.
+    2-D in per-row mode.  Results are bit-identical to the reference's ON CPU TENSORS (fp32, fp16 and
+    bf16): torch's CPU kernels divide by the Python scalar `max_int` with a true division, which is
+    what the kernel does; torch's CUDA kernels turn `x / scalar` into `x * (1 / scalar)`, so the
+    reference run on a GPU can differ from both in the last bit of a scale.
     """
     if q_group_size > 0:
         assert w.shape[-1] % q_group_size == 0

@@ -185,3 +185,45 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["ms_per_step"] < 60e3 and d["config"]["rows"] > 0
     assert "workload" in d["config"]
+
+
+def test_gptq_layer_dealing_is_deterministic_and_balanced():
+    """Row-sharded GPTQ deals the layers of a group to the ranks longest-first by K^3
+    (gptq_quantizer._deal_layers): every rank derives the same assignment without talking."""
+    import gptq_quantizer as gq
+    layers = [(f"l{i}", 4096) for i in range(12)] + [("d0", 11008), ("d1", 11008)]
+    a = gq._deal_layers(layers, 4)
+    b = gq._deal_layers(list(reversed(layers)), 4)
+    assert a == b and set(a.values()) == {0, 1, 2, 3}
+    load = [0.0] * 4
+    for n, k in layers:
+        load[a[n]] += float(k) ** 3
+    assert max(load) / min(load) < 4.0
+    assert a["d0"] != a["d1"]                      # the two wide layers never share a rank
+    assert gq._deal_layers(layers, 1) == {n: 0 for n, _ in layers}
+
+
+def test_bench_sample_slices_and_syrk_fraction_are_fixed_functions():
+    """The CPU arm's row slices are a function of the layer shape only (both arms and every step
+    use the same ones), and the roofline's executed-MMA fraction is the SYRK tile count."""
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("_bench", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.cpu_rows("awq", 4096, 4096) == bench.cpu_rows("awq", 4096, 4096) == 512
+    assert bench.cpu_rows("gptq", 4096, 11008) == 704 and bench.cpu_rows("gptq", 768, 768) == 768
+    assert bench.cpu_rows("pot", 32000, 4096) == 128
+    assert bench.executed_fraction_syrk(4096) == 272 / 512
+    assert abs(bench.executed_fraction_syrk(11008) - 1892 / 3698) < 1e-12
+    assert [n for n, *_ in bench.MODELS["llama2-7b-block"]] == ["attn.qkvo", "mlp.gate_up", "mlp.down"]
+
+
+def test_collective_helpers_are_identities_outside_row_sharding():
+    from b200q import dist as D
+    t = torch.ones(3)
+    assert D.allreduce_sum(t) is t and D.allreduce_max(t) is t and D.broadcast(t, 0) is t
+    assert D.allreduce_sum_async(t) is None and not D.is_sharded() and D.world_size() == 1
+    with D.timed_wait(10), D.on_comm_stream():     # no-ops without a recorder / device
+        pass
+    assert D.WAIT_EVENTS is None
