@@ -11,7 +11,6 @@ from __future__ import annotations
 import gc
 import importlib.util
 import json
-import os
 import sys
 from pathlib import Path
 from typing import Any, Dict, List, Optional, Tuple

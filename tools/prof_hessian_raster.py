@@ -1,7 +1,6 @@
 """Interleaved sweep of the pair kernel's rasterisation band height (B200Q_HESSIAN_RASTER is read
 per call): rounds of [each value: 4 launches] so that clock / power drift hits all values alike."""
 import ctypes
-import os
 import sys
 from pathlib import Path
 REPO = Path(__file__).resolve().parent.parent
