@@ -25,6 +25,7 @@
 // ((q - z) * s, every op rounded to the weight's dtype); for fp32 records the product is formed in
 // fp32 and rounded once to the activation dtype.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <type_traits>
 
@@ -41,8 +42,9 @@ constexpr int A_BYTES = BM * BK * 2;     // 32 KiB
 constexpr int B_BYTES = BN * BK * 2;     // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-constexpr int DQ_PARTS = 2;               // dequant threads per weight row (8 / DQ_PARTS packed words each); measured at 2048x4096x4096: 1 -> 184 us, 2 -> 118 us, 4 -> 172 us
-constexpr int THREADS = 128 + 128 * DQ_PARTS;   // warps 0-3: TMA / MMA / TMEM roles, the rest: dequant + epilogue
+// dequant threads per weight row (8 / DQ_PARTS packed words each), all on the same stage: measured at
+// 2048x4096x4096: 1 -> 184 us, 2 -> 118 us, 4 -> 172 us; see the launch code for the stage-interleaved groups
+// threads = 128 (warps 0-3: TMA / MMA / TMEM roles) + 128 * DQ_PARTS * DQ_GROUPS (dequant + epilogue)
 constexpr uint32_t TMEM_COLS = 128 * MB; // MB accumulators of 128 x 128 fp32
 constexpr int PREFETCH = 3;              // k-blocks of packed codes in flight per dequant thread
 }  // namespace qg
@@ -118,8 +120,8 @@ __device__ __forceinline__ void dequant_word(uint32_t w, const GroupParams<T>& g
   out[3] = __byte_perm(as_u32(h[2]), as_u32(h[3]), 0x7632);
 }
 
-template <typename T, bool REC_F32, bool OUT_F32>
-__global__ void __launch_bounds__(qg::THREADS, 1)
+template <typename T, bool REC_F32, bool OUT_F32, int DQ_PARTS, int DQ_GROUPS>
+__global__ void __launch_bounds__(128 + 128 * DQ_PARTS * DQ_GROUPS, 1)
 w4a16_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __restrict__ qweight,
                   const float* __restrict__ scales, const float* __restrict__ zeros,
                   void* __restrict__ Y, int64_t M, int64_t N, int64_t K, int64_t G) {
@@ -143,7 +145,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __
     tma_prefetch_desc(&tmap_x);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_a[s], 1);
-      mbar_init(&full_b[s], 4 * DQ_PARTS);        // one arrival per dequant warp
+      mbar_init(&full_b[s], 4 * DQ_PARTS);        // one arrival per dequant warp of the group in turn
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(acc_full, 1);
@@ -193,15 +195,18 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __
   } else if (warp >= 4) {
     // ===== dequant producers: DQ_PARTS threads per weight row n0 + r, WPT packed words each =====
     constexpr int WPT = 8 / DQ_PARTS;
+    // The dequant warps form DQ_GROUPS groups that take the k-blocks in turn (group g: k-blocks g,
+    // g + DQ_GROUPS, ...), so that several stages are being produced at once: one stage's chain of
+    // wait -> convert -> st.shared -> fence.proxy.async -> arrive is latency-, not issue-bound.
     const int dq = warp - 4;
     const int r = (dq & 3) * 32 + lane;
-    const int half = dq >> 2;                      // words [WPT * half, WPT * half + WPT) of the k-block
+    const int half = (dq >> 2) % DQ_PARTS;         // words [WPT * half, WPT * half + WPT) of the k-block
+    const int grp = (dq >> 2) / DQ_PARTS;
     const int64_t n = n0 + r;
     const bool row_ok = n < N;
     const uint32_t* qrow = qweight + (row_ok ? n : 0) * words_per_row;
     const float* srow = scales + (row_ok ? n : 0) * groups_per_row;
     const float* zrow = zeros + (row_ok ? n : 0) * groups_per_row;
-    int stage = 0; uint32_t phase = 0;
     int64_t cur_g = -1;
     GroupParams<T> gp;
     gp.set(0.f, 0.f);
@@ -236,18 +241,23 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __
     uint32_t wq[PREFETCH][WPT];
     float sq[PREFETCH], zq[PREFETCH];
 #pragma unroll
-    for (int p = 0; p < PREFETCH; ++p) { sq[p] = 0.f; zq[p] = 0.f; load_words(p, wq[p], sq[p], zq[p]); }
+    for (int p = 0; p < PREFETCH; ++p) {
+      sq[p] = 0.f; zq[p] = 0.f;
+      load_words(grp + p * DQ_GROUPS, wq[p], sq[p], zq[p]);
+    }
     const bool one_group_per_block = (G % BK) == 0;
-    for (int kb0 = 0; kb0 < num_kb; kb0 += PREFETCH) {
+    for (int j0 = 0; grp + j0 * DQ_GROUPS < num_kb; j0 += PREFETCH) {
 #pragma unroll
       for (int p = 0; p < PREFETCH; ++p) {
-        const int kb = kb0 + p;
+        const int kb = grp + (j0 + p) * DQ_GROUPS;
         if (kb < num_kb) {                 // (a predicate, not a break: the slots stay in registers)
+        const int stage = kb % STAGES;
+        const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
         uint32_t w[WPT];
 #pragma unroll
         for (int i = 0; i < WPT; ++i) w[i] = wq[p][i];
         if (one_group_per_block) gp.set(sq[p], zq[p]);
-        load_words(kb + PREFETCH, wq[p], sq[p], zq[p]);   // refill this slot for PREFETCH k-blocks ahead
+        load_words(kb + PREFETCH * DQ_GROUPS, wq[p], sq[p], zq[p]);   // refill: PREFETCH turns ahead
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* brow = smem + stage * STAGE_BYTES + A_BYTES + r * 128;
 #pragma unroll
@@ -268,7 +278,6 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __
         fence_proxy_async_smem();                     // generic-proxy writes -> visible to the MMA
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_b[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -277,7 +286,7 @@ w4a16_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __
     mbar_wait(acc_full, 0);
     tc_fence_after_sync();
 #pragma unroll 1
-    for (int mb = half; mb < MB; mb += DQ_PARTS) {   // one 128-token block per set of four warps
+    for (int mb = (dq >> 2); mb < MB; mb += DQ_PARTS * DQ_GROUPS) {   // one 128-token block per four warps
       const int64_t row = m0 + mb * 128 + q * 32 + lane;
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * 128);
 #pragma unroll 1
@@ -381,12 +390,25 @@ int b200q_w4a16_gemm(const void* X, int64_t M, int64_t K, int act_dtype, const u
   // a record quantised in another dtype than the activations' (fp32, or fp16 vs bf16): the product
   // is formed in fp32 and rounded once
   const bool rec32 = rec_dtype != act_dtype;
+  // dequant configuration: threads per weight row x stage-interleaved groups (B200Q_W4A16_CFG=PG).
+  // Measured at 2048 x 4096 x 4096 / 2048 x 4096 x 11008 (us): 2x1 118.6 / 275.9, 1x2 143.0 / 330.6,
+  // 2x2 111.8 / 223.5 (default), 1x4 146.0 / 318.0.
+  static const int cfg = []() {
+    const char* e = std::getenv("B200Q_W4A16_CFG");
+    const int v = e != nullptr ? std::atoi(e) : 0;
+    return (v == 21 || v == 22) ? v : 22;
+  }();
+#define B200Q_QG_LAUNCH_CFG(T, R, O, P, Gr)                                                            \
+  do {                                                                                                 \
+    cudaFuncSetAttribute(w4a16_gemm_kernel<T, R, O, P, Gr>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                         qg::SMEM_BYTES);                                                              \
+    w4a16_gemm_kernel<T, R, O, P, Gr><<<grid, 128 + 128 * P * Gr, qg::SMEM_BYTES, st>>>(                \
+        tmap, qweight, scales, zeros, Y, M, N, K, G);                                                  \
+  } while (0)
 #define B200Q_QG_LAUNCH(T, R, O)                                                                       \
   do {                                                                                                 \
-    cudaFuncSetAttribute(w4a16_gemm_kernel<T, R, O>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                         qg::SMEM_BYTES);                                                              \
-    w4a16_gemm_kernel<T, R, O><<<grid, qg::THREADS, qg::SMEM_BYTES, st>>>(tmap, qweight, scales, zeros, \
-                                                                          Y, M, N, K, G);              \
+    if (cfg == 21) B200Q_QG_LAUNCH_CFG(T, R, O, 2, 1);                                                 \
+    else B200Q_QG_LAUNCH_CFG(T, R, O, 2, 2);                                                           \
   } while (0)
   if (act_dtype == B200Q_F16) {
     if (rec32) { if (out_f32) B200Q_QG_LAUNCH(__half, true, true); else B200Q_QG_LAUNCH(__half, true, false); }
@@ -396,6 +418,7 @@ int b200q_w4a16_gemm(const void* X, int64_t M, int64_t K, int act_dtype, const u
     else { if (out_f32) B200Q_QG_LAUNCH(__nv_bfloat16, false, true); else B200Q_QG_LAUNCH(__nv_bfloat16, false, false); }
   }
 #undef B200Q_QG_LAUNCH
+#undef B200Q_QG_LAUNCH_CFG
   count_launch();
   return check_launch("w4a16_gemm");
 }
