@@ -84,3 +84,42 @@ def test_smoothquant_hook_survives_packing():
     want = fake(x).float()
     got = Q.pack_model(net, 128)(x).float()
     assert rel(got, want) < 5e-3
+
+
+def test_reference_perplexity_loop_runs_on_the_packed_model():
+    """SURVEY 8(f) item 4 end to end: the reference's own `evaluate_perplexity`
+    (quantization_utils.py:269-322, reached through the drop-in module's pass-through) over a tiny
+    random-init Llama -- once with every nn.Linear fake-quantized by pseudo_quantize_tensor (what
+    the reference evaluates), once with every nn.Linear replaced by a QuantLinear that holds only
+    the packed int4 record and multiplies through the dequant-fused tcgen05 GEMM."""
+    import copy
+    transformers = pytest.importorskip("transformers")
+    import quantization_utils as qu
+    from b200q import build as _build, qlinear as Q
+    if _build.reference_dir() is None:
+        pytest.skip("no reference checkout staged (baseline/_ref): evaluate_perplexity is the reference's code")
+    torch.manual_seed(0)
+    cfg = transformers.LlamaConfig(vocab_size=1000, hidden_size=256, intermediate_size=512,
+                                   num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=4,
+                                   max_position_embeddings=256, tie_word_embeddings=False)
+    model = transformers.LlamaForCausalLM(cfg).half().cuda().eval()
+    fake = copy.deepcopy(model)
+    n_lin = 0
+    for m in fake.modules():
+        if isinstance(m, nn.Linear):
+            m.weight.data = qu.pseudo_quantize_tensor(m.weight.data, 4, 128)
+            n_lin += 1
+    packed = Q.pack_model(copy.deepcopy(model), 128)
+    assert sum(isinstance(m, Q.QuantLinear) for m in packed.modules()) == n_lin == 15
+    assert not any(isinstance(m, nn.Linear) for m in packed.modules())
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(0, 1000, (1, 4 * 128), generator=g)
+    ppl_fake = qu.evaluate_perplexity(fake, None, ids, n_samples=4, block_size=128, verbose=False)
+    ppl_packed = qu.evaluate_perplexity(packed, None, ids, n_samples=4, block_size=128, verbose=False)
+    ppl_raw = qu.evaluate_perplexity(model, None, ids, n_samples=4, block_size=128, verbose=False)
+    assert ppl_fake > 1 and abs(ppl_packed - ppl_fake) / ppl_fake < 2e-3, (ppl_raw, ppl_fake, ppl_packed)
+    # the packed model keeps a quarter of the Linear weight bytes
+    lin_bytes = sum(m.weight.numel() * 2 for m in fake.modules() if isinstance(m, nn.Linear))
+    packed_bytes = sum(b.numel() * b.element_size() for m in packed.modules() if isinstance(m, Q.QuantLinear)
+                       for b in m.buffers())
+    assert packed_bytes < 0.35 * lin_bytes
