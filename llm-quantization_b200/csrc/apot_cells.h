@@ -53,7 +53,11 @@ APOT_HD uint32_t apot_float_bits(float x) {
 // NaN lands in the lowest cell, where the comparison against any threshold is false (index 0,
 // like the reference's argmin over NaN distances).  Result in [1, kApotCells - 1].
 APOT_HD int apot_cell_of(float x, float R, float scale) {
-  const float t = fminf(fmaxf(x, -R), R);
+#if defined(__CUDA_ARCH__)
+  const float t = fminf(fmaxf(x, -R), R);                  // FMNMX: any NaN -> -R
+#else
+  const float t = !(x > -R) ? -R : (x < R ? x : R);        // the same, whatever libm does with sNaN
+#endif
   const float u = fmaf(t, scale, kApotMagic);
   return (int)(apot_float_bits(u) & (uint32_t)(kApotCells - 1));
 }

@@ -5,7 +5,8 @@
 // / pow (POT) or a 31-way nearest search (APOT) plus a row sum of squared errors, and keeps the
 // first candidate with the strictly smallest error.  Here one 8-lane team owns one group, keeps it
 // in registers and runs ALL candidates without touching memory again: HBM traffic is the
-// algorithmic 2 x sizeof(T) bytes per element, the rest is FP32 issue slots.
+// algorithmic 2 x sizeof(T) bytes per element, the rest is FP32 issue slots.  The APOT nearest-level
+// search inside the candidate loop is a table lookup (apot_cells.h) instead of a bisection.
 //
 // Bit-exactness with torch's CPU kernels needs three things, all reproduced literally:
 //   1. rne(log2(r)) / floor(log2(m)) are evaluated as step functions whose step positions come
@@ -18,8 +19,10 @@
 //      for fp32 input and 16 halves (low 8 + high 8, added lane-wise on load) for fp16/bf16 input;
 //      rows shorter than one vector use 4 interleaved scalar accumulators.
 //      tests/test_torch_semantics.py pins these orders against torch itself.
+#include <cstdlib>
 #include <mutex>
 
+#include "apot_cells.h"
 #include "common.cuh"
 
 namespace b200q {
@@ -420,15 +423,38 @@ __device__ __forceinline__ float apot_eval(float wv, float s, const Divisor& sd,
   return ST<T>::rnd(d * d);                                                      // :307
 }
 
-template <typename T, bool EXHAUSTIVE>
+// The same through the cell table (apot_cells.h): one shared-memory read gives the threshold inside
+// x's cell and the two levels it separates, already rounded to the tensor type.
+template <typename T, bool FAST_DIV>
+__device__ __forceinline__ float apot_eval_cells(float wv, float s, const Divisor& sd,
+                                                 const float4* __restrict__ lut, float R, float scale) {
+  const float xn = ST<T>::rnd(FAST_DIV ? sd.div_core(wv) : __fdiv_rn(wv, s));   // w / s_b     :284
+  const float4 e = lut[apot_cell_of(xn, R, scale)];
+  const float q = (xn >= e.x) ? e.z : e.y;                                       // :294-298
+  const float wq = ST<T>::rnd(s * q);                                            // :304
+  const float d = ST<T>::rnd(wv - wq);
+  return ST<T>::rnd(d * d);                                                      // :307
+}
+
+template <typename T, bool EXHAUSTIVE, bool CELLS>
 __global__ void __launch_bounds__(256)
 apot128_kernel(const T* __restrict__ w, T* __restrict__ out, uint8_t* __restrict__ lidx,
                float* __restrict__ best_scale_out, int32_t* __restrict__ best_idx_out,
                int64_t n_groups, LevelParam levels, int L, GridParam grid, int n_grid, float bmin,
-               float bmax) {
+               float bmax, ApotCells cells) {
   __shared__ float lv[32];
+  __shared__ float4 lut[CELLS ? kApotCells : 1];
   if (threadIdx.x < 32) lv[threadIdx.x] = levels.lv[min((int)threadIdx.x, L - 1)];
   __syncthreads();
+  if constexpr (CELLS) {
+    for (int c = threadIdx.x; c < kApotCells; c += blockDim.x) {
+      int base;
+      float thr;
+      apot_cell_entry(cells, c, base, thr);
+      lut[c] = make_float4(thr, ST<T>::rnd(lv[base]), ST<T>::rnd(lv[min(base + 1, L - 1)]), 0.f);
+    }
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int l = lane & 7;
   const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
@@ -461,7 +487,17 @@ apot128_kernel(const T* __restrict__ w, T* __restrict__ out, uint8_t* __restrict
     const Divisor sd(s);
     float sq[16];
     int idx;
-    if (fast) {
+    if constexpr (CELLS) {
+      if (fast) {
+#pragma unroll
+        for (int v = 0; v < 16; ++v)
+          sq[v] = apot_eval_cells<T, true>(x[v], s, sd, lut, cells.R, cells.scale);
+      } else {
+#pragma unroll
+        for (int v = 0; v < 16; ++v)
+          sq[v] = apot_eval_cells<T, false>(x[v], s, sd, lut, cells.R, cells.scale);
+      }
+    } else if (fast) {
 #pragma unroll
       for (int v = 0; v < 16; ++v) sq[v] = apot_eval<T, EXHAUSTIVE, true>(x[v], s, sd, lv, L, idx);
     } else {
@@ -598,6 +634,14 @@ int b200q_apot_quant(const void* w, void* out, uint8_t* level_idx, float* best_s
   }
   // bracket search is exact only for strictly increasing levels spaced well above ulp(101)
   const bool exhaustive = !sorted || (n_levels > 1 && min_gap < 6.2e-5f);
+  // G == 128: the candidate loop finds the nearest level through the cell table when the level
+  // set allows it (apot_cells.h; every reference level set with k <= 2 does); B200Q_APOT_CELLS=0
+  // keeps the bisecting kernel (A/B timing)
+  const char* cells_env = getenv("B200Q_APOT_CELLS");       // read per call: A/B inside one process
+  const bool cells_enabled = !(cells_env && cells_env[0] == '0');
+  ApotCells cells;
+  const bool use_cells = apot_build_cells(levels_host, n_levels, cells) && !exhaustive &&
+                         cells_enabled && n_levels > 1;
   GridParam gp;
   float bmin, bmax;
   grid_param(gp, grid_host, n_grid, bmin, bmax);
@@ -607,11 +651,17 @@ int b200q_apot_quant(const void* w, void* out, uint8_t* level_idx, float* best_s
     if (group == 128) {
       const int64_t blocks = (n_groups + 31) / 32;
       if (exhaustive)
-        apot128_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(
-            wt, ot, level_idx, best_scale, best_idx, n_groups, lp, n_levels, gp, n_grid, bmin, bmax);
+        apot128_kernel<T, true, false><<<(unsigned)blocks, 256, 0, st>>>(
+            wt, ot, level_idx, best_scale, best_idx, n_groups, lp, n_levels, gp, n_grid, bmin, bmax,
+            cells);
+      else if (use_cells)
+        apot128_kernel<T, false, true><<<(unsigned)blocks, 256, 0, st>>>(
+            wt, ot, level_idx, best_scale, best_idx, n_groups, lp, n_levels, gp, n_grid, bmin, bmax,
+            cells);
       else
-        apot128_kernel<T, false><<<(unsigned)blocks, 256, 0, st>>>(
-            wt, ot, level_idx, best_scale, best_idx, n_groups, lp, n_levels, gp, n_grid, bmin, bmax);
+        apot128_kernel<T, false, false><<<(unsigned)blocks, 256, 0, st>>>(
+            wt, ot, level_idx, best_scale, best_idx, n_groups, lp, n_levels, gp, n_grid, bmin, bmax,
+            cells);
     } else {
       const int64_t blocks = std::min<int64_t>((n_groups + 7) / 8, (int64_t)kNumSMs * 32);
       if (exhaustive)
