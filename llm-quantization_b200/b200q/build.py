@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every .cu under csrc/ for sm_100a and link libb200quant.so. Returns its path."""
     nvcc = _nvcc()
     OBJ_DIR.mkdir(exist_ok=True)
-    headers = list(CSRC.glob("*.cuh")) + [REPO / "include" / "b200quant.h"]
+    headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [REPO / "include" / "b200quant.h"]
     objs = []
     log_lines = []
     jobs = []
