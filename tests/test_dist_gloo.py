@@ -83,6 +83,23 @@ def _worker(rank: int, world: int, port: int, ret):
             loss = D.allreduce_sum(O.awq_search_losses(Ws, H, sal, 4, 128, cands).float())
             torch.testing.assert_close(loss.double(), O.awq_search_losses(W, H, sal, 4, 128, cands),
                                        rtol=1e-5, atol=0)
+            # the packed symmetric exchange (tensor_ops._exchange_folded) in torch: every rank packs
+            # the lower triangle of its partial, reduce-scatter -> each rank owns the sum of one
+            # slice -> all-gather; unpacked and mirrored it is the all-reduced matrix
+            part = torch.randn(K, K, generator=torch.Generator().manual_seed(100 + rank))
+            part = part + part.T
+            il = torch.tril_indices(K, K)
+            packed = part[il[0], il[1]]
+            per = (packed.numel() + world - 1) // world
+            padded = torch.zeros(per * world)
+            padded[:packed.numel()] = packed
+            mine = D.reduce_scatter_sum(torch.empty(per), padded)
+            whole = D.all_gather_into(torch.empty(per * world), mine)[:packed.numel()]
+            full = torch.zeros(K, K)
+            full[il[0], il[1]] = whole
+            full = full + full.T - torch.diag(torch.diag(full))
+            torch.testing.assert_close(full, D.allreduce_sum(part.clone()), rtol=1e-6, atol=1e-6)
+            assert not D.backend_is_nccl()
         assert not D.is_sharded()
         ret[rank] = "ok"
     finally:
